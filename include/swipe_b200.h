@@ -1,0 +1,166 @@
+/*
+ * swipe_b200.h -- C ABI of the B200 (sm_100a) score-only Smith-Waterman scan.
+ *
+ * This is the drop-in boundary for the search path of torognes/swipe.  The reference has no
+ * plugin interface; its seam is four free functions that search_chunk() calls
+ * (reference swipe.h:200-258, call sites swipe.cc:1432-1455, :1499-1510, :1578-1585):
+ *
+ *     search7 / search7_ssse3   (swipe.h:200-222)   7-bit pass over a list of subjects
+ *     search16                  (swipe.h:224-235)   16-bit pass over the survivors
+ *     fullsw                    (swipe.h:251-258)   63-bit pass over what is left
+ *     search16s                 (swipe.h:237-249)   16-bit pass that also reports the end cell
+ *
+ * A GPU cannot be fed at the reference's per-chunk granularity (a few hundred subjects,
+ * swipe.cc:479-481), so the boundary sits one level up: "search_chunk over a whole database
+ * shard" with the width cascade hidden inside.  The observable output of that cascade is the
+ * exact 63-bit score of every subject (anything at or above a width's limit is discarded and
+ * recomputed, swipe.cc:1464, :1519), and that is what these entry points return.
+ *
+ * Conventions
+ *   - plain C linkage, plain pointers and sizes, no exceptions cross the boundary;
+ *   - every function returns SWB_OK (0) or a negative swb_status; swb_strerror() names it.  The
+ *     reference reports every error through fatal() -> exit(1) (swipe.cc:158-170); the host shim
+ *     keeps that behaviour by calling fatal(swb_strerror(rc)) on a non-zero status;
+ *   - the caller owns every buffer it passes; the library owns what swb_db_open returns;
+ *   - host pointers unless a parameter says "device";
+ *   - one host thread per handle at a time; different handles (one per GPU) may be driven
+ *     concurrently from different threads, like the reference's per-thread search_data.
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute call fails with
+ *     SWB_ERR_NO_DEVICE / SWB_ERR_CUDA.
+ */
+#ifndef SWIPE_B200_H
+#define SWIPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWB_ABI_VERSION 1
+#define SWB_MATRIX_DIM 32 /* reference swipe.h:66-68: score tables are 32 x 32 */
+
+typedef enum swb_status
+{
+  SWB_OK = 0,
+  SWB_ERR_ARG = -1,       /* null pointer, negative size, symbol code > 31, bad offsets */
+  SWB_ERR_NO_DEVICE = -2, /* no CUDA device / not an sm_100 part */
+  SWB_ERR_CUDA = -3,      /* a CUDA runtime call failed; swb_last_cuda_error() has the text */
+  SWB_ERR_NOMEM = -4,
+  SWB_ERR_RANGE = -5,     /* scoring parameters outside what the kernels represent exactly */
+  SWB_ERR_INTERNAL = -6
+} swb_status;
+
+/* Scoring parameters, exactly the values the reference hands its kernels.
+ *   matrix          : 32 x 32 scores indexed [(db_symbol << 5) + query_symbol], the layout of
+ *                     the reference's score_matrix_63 (matrices.cc:531-538, search63.cc:52-58).
+ *   gap_open_extend : penalty of the first gap position = open + extend (swipe.cc:1126; this is
+ *                     what search7/search16/fullsw receive as "gap_open_penalty").
+ *   gap_extend      : penalty of each further gap position.                                   */
+typedef struct swb_scoring
+{
+  const int64_t *matrix;
+  int64_t gap_open_extend;
+  int64_t gap_extend;
+} swb_scoring;
+
+/* Per-search bookkeeping, mirroring the reference's counters compute7/compute16/compute63
+ * (swipe.cc:111-119, bumped at :1425, :1494, :1552) plus what the GPU path adds.             */
+typedef struct swb_counters
+{
+  int64_t subjects;       /* subjects scored by this call                                      */
+  int64_t cells;          /* sum(subject length) * qlen: numerator of the reference's GCUPS    */
+  int64_t ref_width7;     /* subjects the reference would have kept from its 7-bit pass        */
+  int64_t ref_width16;    /* ... from its 16-bit pass                                          */
+  int64_t ref_width63;    /* ... from fullsw                                                   */
+  int64_t gpu_narrow;     /* subjects finished by the packed 16-bit-lane kernel                */
+  int64_t gpu_requeued;   /* subjects whose lane reached the overflow limit, redone wide       */
+  int64_t kernel_launches;/* CUDA kernels launched by this call                                */
+  double scan_ms;         /* device time of the scan kernels (CUDA events on the handle stream)*/
+  double requeue_ms;      /* device time of the wide re-queue kernels                          */
+} swb_counters;
+
+typedef struct swb_db swb_db; /* opaque: one database shard resident on one GPU */
+
+/* ---- library / device ------------------------------------------------------------------- */
+int swb_abi_version(void);
+const char *swb_strerror(int status);
+const char *swb_last_cuda_error(void);              /* text of the last CUDA failure (thread local) */
+int swb_device_count(int *count);                    /* SWB_ERR_NO_DEVICE when there is none  */
+
+/* Pinned host memory for callers that want full-speed uploads (optional). */
+int swb_host_alloc(void **ptr, int64_t bytes);
+int swb_host_free(void *ptr);
+
+/* ---- database shard ----------------------------------------------------------------------
+ * Replaces db_mapsequences + the db_getsequence pulls the reference kernels make while they
+ * run (search7.cc:899-917, database.cc:1082-1131, :1237-1401): the shard is uploaded once and
+ * re-laid-out on the device (length-sorted, two subjects per 32-bit lane pair, 4 columns per
+ * block) so that the scan kernels stream it with coalesced loads.
+ *
+ *   residues : symbol codes 0..31 (protein: NCBIstdaa as stored in a .psq, query.cc:178;
+ *              nucleotide: the reference's 4-bit one-hot codes, database.cc:915-921)
+ *   offsets  : nseq+1 byte offsets into residues; subject i occupies
+ *              residues[offsets[i] .. offsets[i+1] - trailing)
+ *   trailing : bytes to drop at the end of every subject: 1 when offsets index a raw .psq
+ *              (NUL separators, database.cc:1246-1248, search7.cc:916), 0 for packed input
+ *   stream   : a cudaStream_t (as void*) all work of this handle is issued on, or NULL for a
+ *              stream the handle creates itself
+ */
+int swb_db_open(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
+                int trailing, void *stream, swb_db **db);
+int swb_db_close(swb_db *db);
+int swb_db_info(const swb_db *db, int64_t *nseq, int64_t *total_residues, int64_t *longest);
+
+/* ---- the hot path ------------------------------------------------------------------------
+ * swb_search: what search_chunk's cascade (swipe.cc:1416-1594) yields for every subject of the
+ * shard: scores[i] = exact affine-gap local alignment score of the query against subject i, in
+ * the order the subjects were given to swb_db_open.  query holds symbol codes 0..31
+ * (query.cc:317-325).  counters may be NULL.
+ */
+int swb_search(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
+               int64_t *scores, swb_counters *counters);
+
+/* swb_search_list: the same for a list of subjects given the way the reference's kernels take
+ * it -- codes (seqno << 3) | (strand << 2) | frame (swipe.cc:1373-1391); strand and frame must
+ * be 0 here (protein / forward-strand database symbols).  scores[k] belongs to seqnos[k], the
+ * contract of search7/search16 (search7.cc:894-895).
+ */
+int swb_search_list(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
+                    const int64_t *seqnos, int64_t n, int64_t *scores, swb_counters *counters);
+
+/* swb_search_end: search16s's contract (swipe.h:237-249, search16s.cc:390-405, called from
+ * align_chunk swipe.cc:381-393): exact score plus the alignment end -- bestpos = first subject
+ * column (0-based) in which the maximum is reached, bestq = smallest query row reaching it in
+ * that column; both -1 when the score is 0.  Scores are exact (never saturated at 65535).
+ */
+int swb_search_end(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
+                   const int64_t *seqnos, int64_t n, int64_t *scores, int64_t *bestpos,
+                   int64_t *bestq);
+
+/* ---- the sink ----------------------------------------------------------------------------
+ * swb_topk_merge: the insertion rule of hits_enter (hits.cc:163-222) applied to the scores of
+ * one or more shards: reject score < min_score or > upper_score, order by score descending then
+ * seqno descending, keep at most `keep` entries; totalhits / obvious as hits.cc:174-178.
+ * shard k contributes n[k] subjects whose global sequence numbers are seqno_base[k] + i.
+ * Returns the number of hits kept (>= 0) or a negative status.
+ */
+int64_t swb_topk_merge(int nshards, const int64_t *const *scores, const int64_t *n,
+                       const int64_t *seqno_base, int64_t keep, int64_t min_score,
+                       int64_t upper_score, int64_t *out_seqno, int64_t *out_score,
+                       int64_t *totalhits, int64_t *obvious);
+
+/* ---- tuning / introspection (not part of the reference's surface) -------------------------- */
+/* Forces every subject through one kernel family: 0 = cascade (default), 1 = packed 16-bit
+ * lanes only is not allowed (would not be exact) -> rejected; 2 = wide kernel for everything.  */
+int swb_set_mode(swb_db *db, int mode);
+/* Device time of the last swb_db_open's upload + re-layout, in ms. */
+int swb_db_open_ms(const swb_db *db, double *upload_ms, double *layout_ms);
+/* Test hook: pin the scan kernel shape (G threads per stream, R query rows per thread) and the
+ * lane arithmetic (0 = DPX int16 only, 1 = DPX + fp16-pattern adds); (0, 0, -1) = automatic.   */
+int swb_set_shape(swb_db *db, int G, int R, int lane_mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIPE_B200_H */

@@ -1,0 +1,254 @@
+"""ctypes binding of include/swipe_b200.h (the C ABI is the product; this is plumbing)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+STATUS = {0: "SWB_OK", -1: "SWB_ERR_ARG", -2: "SWB_ERR_NO_DEVICE", -3: "SWB_ERR_CUDA",
+          -4: "SWB_ERR_NOMEM", -5: "SWB_ERR_RANGE", -6: "SWB_ERR_INTERNAL"}
+
+# every symbol include/swipe_b200.h declares (tests check the library exports all of them)
+EXPORTS = ["swb_abi_version", "swb_strerror", "swb_last_cuda_error", "swb_device_count",
+           "swb_host_alloc", "swb_host_free", "swb_db_open", "swb_db_close", "swb_db_info",
+           "swb_search", "swb_search_list", "swb_search_end", "swb_topk_merge", "swb_set_mode",
+           "swb_db_open_ms", "swb_set_shape"]
+
+
+class SwbError(RuntimeError):
+    def __init__(self, status, detail=""):
+        self.status = status
+        msg = "%s (%d)" % (STATUS.get(status, "?"), status)
+        if detail:
+            msg += ": " + detail
+        super().__init__(msg)
+
+
+class _Scoring(C.Structure):
+    _fields_ = [("matrix", C.POINTER(C.c_int64)), ("gap_open_extend", C.c_int64),
+                ("gap_extend", C.c_int64)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("subjects", C.c_int64), ("cells", C.c_int64), ("ref_width7", C.c_int64),
+                ("ref_width16", C.c_int64), ("ref_width63", C.c_int64), ("gpu_narrow", C.c_int64),
+                ("gpu_requeued", C.c_int64), ("kernel_launches", C.c_int64),
+                ("scan_ms", C.c_double), ("requeue_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def load_library():
+    """Loads (building first if stale and nvcc is present) the CUDA library.  Raises when it is
+    missing: there is deliberately no fallback implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.build_lib()
+    if not os.path.exists(path):
+        raise RuntimeError("swipe_b200: %s is not built (run python -m swipe_b200.build)" % path)
+    lib = C.CDLL(path)
+    p64 = C.POINTER(C.c_int64)
+    pu8 = C.POINTER(C.c_uint8)
+    lib.swb_abi_version.restype = C.c_int
+    lib.swb_strerror.restype = C.c_char_p
+    lib.swb_strerror.argtypes = [C.c_int]
+    lib.swb_last_cuda_error.restype = C.c_char_p
+    lib.swb_device_count.argtypes = [C.POINTER(C.c_int)]
+    lib.swb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
+    lib.swb_host_free.argtypes = [C.c_void_p]
+    lib.swb_db_open.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                C.POINTER(C.c_void_p)]
+    lib.swb_db_close.argtypes = [C.c_void_p]
+    lib.swb_db_info.argtypes = [C.c_void_p, p64, p64, p64]
+    lib.swb_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Scoring), C.c_void_p,
+                               C.POINTER(Counters)]
+    lib.swb_search_list.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Scoring),
+                                    C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Counters)]
+    lib.swb_search_end.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Scoring),
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.swb_topk_merge.restype = C.c_int64
+    lib.swb_topk_merge.argtypes = [C.c_int, C.POINTER(C.c_void_p), p64, p64, C.c_int64, C.c_int64,
+                                   C.c_int64, C.c_void_p, C.c_void_p, p64, p64]
+    lib.swb_set_mode.argtypes = [C.c_void_p, C.c_int]
+    lib.swb_db_open_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.swb_set_shape.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    for name in ("swb_device_count", "swb_host_alloc", "swb_host_free", "swb_db_open",
+                 "swb_db_close", "swb_db_info", "swb_search", "swb_search_list", "swb_search_end",
+                 "swb_set_mode", "swb_db_open_ms", "swb_set_shape"):
+        getattr(lib, name).restype = C.c_int
+    _LIB = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        lib = load_library()
+        detail = lib.swb_strerror(rc).decode()
+        cuda = lib.swb_last_cuda_error().decode()
+        if rc in (-2, -3, -4) and cuda:
+            detail += " [" + cuda + "]"
+        raise SwbError(rc, detail)
+
+
+def device_count():
+    lib = load_library()
+    n = C.c_int(0)
+    _check(lib.swb_device_count(C.byref(n)))
+    return n.value
+
+
+class HostBuffer:
+    """Pinned host memory from swb_host_alloc, viewed as a numpy array."""
+
+    def __init__(self, nbytes):
+        lib = load_library()
+        self._ptr = C.c_void_p()
+        _check(lib.swb_host_alloc(C.byref(self._ptr), int(nbytes)))
+        self.nbytes = int(nbytes)
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self._ptr.value)
+        self.u8 = np.frombuffer(buf, dtype=np.uint8, count=self.nbytes)
+
+    def view(self, dtype):
+        return self.u8.view(dtype)
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            load_library().swb_host_free(self._ptr)
+            self._ptr = None
+            self.u8 = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Scoring:
+    """matrix: int64[1024] indexed [(db_symbol << 5) + query_symbol] (score_matrix_63 layout);
+    gap_open / gap_extend as given on the reference's command line (-G / -E)."""
+
+    def __init__(self, matrix, gap_open, gap_extend):
+        self.matrix = np.ascontiguousarray(matrix, dtype=np.int64).reshape(-1)
+        if self.matrix.size != 1024:
+            raise ValueError("matrix must hold 32 x 32 scores")
+        self.gap_open = int(gap_open)
+        self.gap_extend = int(gap_extend)
+
+    def _c(self):
+        s = _Scoring()
+        s.matrix = self.matrix.ctypes.data_as(C.POINTER(C.c_int64))
+        s.gap_open_extend = self.gap_open + self.gap_extend     # swipe.cc:1126
+        s.gap_extend = self.gap_extend
+        return s
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+class Database:
+    """One database shard resident on one GPU (swb_db)."""
+
+    def __init__(self, residues, offsets, device=0, trailing=0, stream=None):
+        lib = load_library()
+        self._lib = lib
+        self._residues = _u8(residues)
+        self._offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.nseq = int(self._offsets.size - 1)
+        self._h = C.c_void_p()
+        _check(lib.swb_db_open(int(device), self._residues.ctypes.data, self._offsets.ctypes.data,
+                               self.nseq, int(trailing), C.c_void_p(stream or 0),
+                               C.byref(self._h)))
+        self.last_counters = None
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._lib.swb_db_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _check(self._lib.swb_db_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"nseq": a.value, "residues": b.value, "longest": c.value}
+
+    def open_ms(self):
+        a, b = C.c_double(), C.c_double()
+        _check(self._lib.swb_db_open_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_mode(self, mode):
+        _check(self._lib.swb_set_mode(self._h, int(mode)))
+
+    def set_shape(self, G=0, R=0, lane_mode=-1):
+        _check(self._lib.swb_set_shape(self._h, int(G), int(R), int(lane_mode)))
+
+    def search(self, query, scoring, out=None):
+        q = _u8(query)
+        scores = out if out is not None else np.empty(self.nseq, dtype=np.int64)
+        ctr = Counters()
+        sc = scoring._c()
+        _check(self._lib.swb_search(self._h, q.ctypes.data, q.size, C.byref(sc),
+                                    scores.ctypes.data, C.byref(ctr)))
+        self.last_counters = ctr.as_dict()
+        return scores
+
+    def search_list(self, query, scoring, seqnos):
+        """seqnos: plain sequence numbers; coded (seqno << 3) for the ABI as the reference does."""
+        q = _u8(query)
+        coded = np.ascontiguousarray(np.asarray(seqnos, dtype=np.int64) << 3)
+        scores = np.empty(coded.size, dtype=np.int64)
+        ctr = Counters()
+        sc = scoring._c()
+        _check(self._lib.swb_search_list(self._h, q.ctypes.data, q.size, C.byref(sc),
+                                         coded.ctypes.data, coded.size, scores.ctypes.data,
+                                         C.byref(ctr)))
+        self.last_counters = ctr.as_dict()
+        return scores
+
+    def search_end(self, query, scoring, seqnos):
+        q = _u8(query)
+        coded = np.ascontiguousarray(np.asarray(seqnos, dtype=np.int64) << 3)
+        scores = np.empty(coded.size, dtype=np.int64)
+        bestpos = np.empty(coded.size, dtype=np.int64)
+        bestq = np.empty(coded.size, dtype=np.int64)
+        sc = scoring._c()
+        _check(self._lib.swb_search_end(self._h, q.ctypes.data, q.size, C.byref(sc),
+                                        coded.ctypes.data, coded.size, scores.ctypes.data,
+                                        bestpos.ctypes.data, bestq.ctypes.data))
+        return scores, bestpos, bestq
+
+
+def topk_merge(score_arrays, seqno_bases, keep, min_score=0, upper_score=2 ** 62):
+    """hits_enter's rule (hits.cc:163-222) over the score arrays of one or more shards."""
+    lib = load_library()
+    arrs = [np.ascontiguousarray(a, dtype=np.int64) for a in score_arrays]
+    n = len(arrs)
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+    ns = (C.c_int64 * max(n, 1))(*[a.size for a in arrs])
+    bases = (C.c_int64 * max(n, 1))(*[int(b) for b in seqno_bases])
+    out_seq = np.empty(max(keep, 1), dtype=np.int64)
+    out_sc = np.empty(max(keep, 1), dtype=np.int64)
+    tot, obv = C.c_int64(), C.c_int64()
+    k = lib.swb_topk_merge(n, ptrs, ns, bases, int(keep), int(min_score), int(upper_score),
+                           out_seq.ctypes.data, out_sc.ctypes.data, C.byref(tot), C.byref(obv))
+    if k < 0:
+        _check(int(k))
+    return out_seq[:k].copy(), out_sc[:k].copy(), tot.value, obv.value

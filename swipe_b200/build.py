@@ -1,0 +1,61 @@
+"""Builds the in-tree native code: the sm_100a CUDA library behind include/swipe_b200.h and,
+for tests / bench baselines only, the CPU oracle under oracle/."""
+import os
+import shutil
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "swipe_b200", "csrc")
+LIB = os.path.join(CSRC, "libswipe_b200.so")
+SOURCES = ["swb_api.cu"]
+DEPS = ["swb_api.cu", "sw_kernels.cuh", os.path.join(ROOT, "include", "swipe_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    for d in deps:
+        p = d if os.path.isabs(d) else os.path.join(CSRC, d)
+        if os.path.exists(p) and os.path.getmtime(p) > t:
+            return True
+    return False
+
+
+def build_lib(force=False, verbose=False):
+    """Compile swipe_b200/csrc/libswipe_b200.so for sm_100a (cross-compiles without a GPU)."""
+    if not force and not _stale(LIB, DEPS):
+        return LIB
+    nvcc = _nvcc()
+    if nvcc is None:
+        if os.path.exists(LIB):
+            return LIB
+        raise RuntimeError("nvcc not found and %s is not built" % LIB)
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    subprocess.run(cmd, cwd=CSRC, check=True)
+    return LIB
+
+
+def build_oracle():
+    """TEST INFRASTRUCTURE: the plain-C oracle and, where /root/reference exists, the unmodified
+    reference kernels under oracle/_ref (see oracle/Makefile)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"], check=True)
+
+
+if __name__ == "__main__":
+    import sys
+    build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_oracle()
+    print(LIB)

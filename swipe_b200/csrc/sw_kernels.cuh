@@ -1,0 +1,433 @@
+// sw_kernels.cuh -- sm_100a kernels of the score-only affine-gap Smith-Waterman scan.
+//
+// Reference behaviour being reproduced (torognes/swipe): the recurrence of fullsw
+// (search63.cc:28-89) evaluated for every database subject, which is what the reference's
+// 7-bit -> 16-bit -> 63-bit cascade (search7.cc:755-958, search16.cc:320-546,
+// swipe.cc:1416-1594) delivers.  Nothing here is derived from the reference's SSE code; the
+// design is a systolic, register-resident scan built for the B200 SM:
+//
+//   * two subjects share every 32-bit register as 16-bit lanes (DPX s16x2 instructions:
+//     VIADDMNMX / VIMNMX3 do add+max and 3-way max in one issue);
+//   * a group of G threads owns one *stream* of subject pairs; thread g keeps the H and E
+//     values of query rows [g*R, g*R+R) in registers for the whole scan (no spill of the DP
+//     column), and the group works as a pipeline: at step t thread g processes the 4-column
+//     block t-g of the stream, handing the bottom H/F of its strip to thread g+1 by shuffle;
+//   * subjects follow each other in the stream without draining the pipeline (a START flag on
+//     a block resets the strip), so the fill/drain cost is paid once per stream, not per subject;
+//   * substitution scores come from a per-block table built once per 4 columns in shared memory
+//     (row = query symbol, 4 words = the 4 columns, each word = the two lanes' scores) and
+//     shared by all G threads, so the inner loop does one conflict-free LDS.128 per 4 cell
+//     pairs and no byte shuffling;
+//   * queries longer than G*R rows are scanned in passes; the bottom row of a pass is kept in
+//     global memory (32 B per block) and fed to thread 0 in the next pass.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+#define SWB_PAD_CODE 32      // internal subject symbol for padding columns (scores SWB_PAD_SCORE)
+#define SWB_PAD_SCORE (-1)
+#define SWB_MROWS 33         // 32 symbol codes + the pad code
+#define SWB_SMEM_HEADER 2176  // the [33][32] s16 table, rounded up to 128 B
+#define SWB_FLAG_START 1u
+#define SWB_FLAG_END 2u
+
+enum { SWB_MODE_INT16 = 0, SWB_MODE_HYBRID = 1 };
+
+struct ScanParams
+{
+  const uint2 *blocks;        // [total_blocks] 8 residues each: bytes 0-3 lane A cols 0-3, 4-7 lane B
+  const long long *pairblk;   // [npairs+1] exclusive prefix of blocks per pair
+  const int *stream_pair;     // [nstreams+1] first pair of every stream
+  u32 *pair_scores;           // [npairs] packed lane maxima
+  const short *m16;           // [33][32] score of (subject code, table row) in the mode's encoding
+  const unsigned short *qrow_off; // [npass*G*R] byte offset of every query row's table row
+  uint4 *bndH;                // [total_blocks] bottom H of a pass (only when npass > 1)
+  uint4 *bndF;
+  int nq;                     // table rows in use (distinct query symbols)
+  int slot_bytes;             // (nq + 2) * 16: rows, header row, pad row
+  int npass;
+  u32 negq;                   // both lanes: -(gap open + extend) in the mode's encoding
+  u32 negr;                   // both lanes: -(gap extend), two's complement
+  u32 padword;                // both lanes: score of a padding query row
+};
+
+__device__ __forceinline__ u32 swb_hadd2(u32 a, u32 b)
+{
+  u32 r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+// One DP cell for both lanes.  hd = H(i-1,j-1), s = score word, e = E(i,j), f = F(i,j).
+// Produces h = H(i,j) and advances e -> E(i,j+1), f -> F(i+1,j); smax accumulates max H.
+template <int MODE>
+__device__ __forceinline__ void swb_cell(u32 hd, u32 s, u32 &e, u32 &f, u32 &h, u32 &smax,
+                                         const u32 negq, const u32 negr)
+{
+  if (MODE == SWB_MODE_INT16)
+  {
+    u32 t = __viaddmax_s16x2(hd, s, e);        // max(hd + s, e)
+    h = __vimax_s16x2_relu(t, f);              // max(.., f, 0)
+    smax = __vmaxs2(smax, h);
+    u32 hq = __vadd2(h, negq);                 // h - (open + extend)
+    e = __viaddmax_s16x2(e, negr, hq);         // max(e - extend, h - open - extend)
+    f = __viaddmax_s16x2(f, negr, hq);
+  }
+  else
+  {
+    // Values 0..2047 are their own fp16 bit patterns (value n * 2^-24), so an fp16x2 add is an
+    // exact integer add there and runs on the FMA pipe beside the DPX ops on the ALU pipe.
+    // Negative results come out sign-magnitude, i.e. as large negative s16 values, and are
+    // removed by the relu of the following max.
+    u32 a = swb_hadd2(hd, s);
+    h = __vimax3_s16x2_relu(a, e, f);
+    smax = __vmaxs2(smax, h);
+    u32 hq = swb_hadd2(h, negq);
+    e = __viaddmax_s16x2_relu(e, negr, hq);
+    f = __viaddmax_s16x2_relu(f, negr, hq);
+  }
+}
+
+template <int G, int R, int MODE>
+__global__ void __launch_bounds__(128) swb_scan_kernel(const ScanParams P)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned short *Ms = (unsigned short *)smem;       // [33][32]
+  unsigned char *ring_base = smem + SWB_SMEM_HEADER;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int g = lane % G;
+  const int grp = lane / G;
+  const int nq = P.nq;
+  const int slot_bytes = P.slot_bytes;
+
+  for (int i = threadIdx.x; i < SWB_MROWS * 32 / 2; i += blockDim.x)
+    ((u32 *)Ms)[i] = ((const u32 *)P.m16)[i];
+
+  unsigned char *ring = ring_base + (size_t)((warp * (32 / G) + grp) * G) * slot_bytes;
+  // the pad row of every slot is written once; builds never touch it
+  *(uint4 *)(ring + g * slot_bytes + (nq + 1) * 16) =
+      make_uint4(P.padword, P.padword, P.padword, P.padword);
+  __syncthreads();
+
+  const int stream = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 / G) + grp;
+  const int p0 = P.stream_pair[stream];
+  const int p1 = P.stream_pair[stream + 1];
+  const long long b0 = P.pairblk[p0];
+  const int nblk = (int)(P.pairblk[p1] - b0);
+  const uint2 *blk = P.blocks + b0;
+  const int nsteps_warp = __reduce_max_sync(0xffffffffu, nblk);
+  const int nsteps = nsteps_warp > 0 ? nsteps_warp + G - 1 : 0;
+  const u32 negq = P.negq, negr = P.negr;
+
+  for (int pass = 0; pass < P.npass; pass++)
+  {
+    u32 rq[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) rq[i] = P.qrow_off[(pass * G + g) * R + i];
+
+    u32 H[R], E[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) { H[i] = 0; E[i] = 0; }
+    u32 smax = 0, dtop = 0;
+    u32 ih0 = 0, ih1 = 0, ih2 = 0, ih3 = 0, if0 = 0, if1 = 0, if2 = 0, if3 = 0, is = 0;
+    int pair_out = p0;
+    const bool feed = (pass > 0) && (g == 0);          // thread 0 reads the previous pass's bottom row
+    const bool spill = (pass + 1 < P.npass) && (g == G - 1);
+
+    uint2 cur = make_uint2(0, 0);
+    if (nblk > 0) cur = blk[0];
+
+    for (int t = 0; t < nsteps; t++)
+    {
+      uint2 nxt = make_uint2(0, 0);
+      if (t + 1 < nblk) nxt = blk[t + 1];
+
+      // ---- build the score table of block t into slot t % G ---------------------------------
+      if (t < nblk)
+      {
+        unsigned char *slot = ring + (t & (G - 1)) * slot_bytes;
+        const u32 a0 = (cur.x & 63u) * 32u, a1 = ((cur.x >> 8) & 63u) * 32u,
+                  a2 = ((cur.x >> 16) & 63u) * 32u, a3 = ((cur.x >> 24) & 63u) * 32u;
+        const u32 c0 = (cur.y & 63u) * 32u, c1 = ((cur.y >> 8) & 63u) * 32u,
+                  c2 = ((cur.y >> 16) & 63u) * 32u, c3 = ((cur.y >> 24) & 63u) * 32u;
+        for (int s = g; s < nq; s += G)
+        {
+          uint4 w;
+          w.x = __byte_perm(Ms[a0 + s], Ms[c0 + s], 0x5410);
+          w.y = __byte_perm(Ms[a1 + s], Ms[c1 + s], 0x5410);
+          w.z = __byte_perm(Ms[a2 + s], Ms[c2 + s], 0x5410);
+          w.w = __byte_perm(Ms[a3 + s], Ms[c3 + s], 0x5410);
+          *(uint4 *)(slot + s * 16) = w;
+        }
+        if (g == 0) *(u32 *)(slot + nq * 16) = (cur.x >> 6) & 3u;
+      }
+      __syncwarp();
+
+      // ---- thread g works on block t - g -------------------------------------------------------
+      const int b = t - g;
+      u32 hup0 = 0, hup1 = 0, hup2 = 0, hup3 = 0, f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+      if (b >= 0 && b < nblk)
+      {
+        const unsigned char *slot = ring + (b & (G - 1)) * slot_bytes;
+        const u32 flags = *(const u32 *)(slot + nq * 16);
+        if (feed)
+        {
+          const uint4 vh = P.bndH[b0 + b], vf = P.bndF[b0 + b];
+          ih0 = vh.x; ih1 = vh.y; ih2 = vh.z; ih3 = vh.w;
+          if0 = vf.x; if1 = vf.y; if2 = vf.z; if3 = vf.w;
+        }
+        if (flags & SWB_FLAG_START)
+        {
+#pragma unroll
+          for (int i = 0; i < R; i++) { H[i] = 0; E[i] = 0; }
+          smax = 0;
+          dtop = 0;
+        }
+        smax = __vmaxs2(smax, is);
+        hup0 = ih0; hup1 = ih1; hup2 = ih2; hup3 = ih3;
+        f0 = if0; f1 = if1; f2 = if2; f3 = if3;
+        u32 dg = dtop;
+#pragma unroll
+        for (int i = 0; i < R; i++)
+        {
+          const uint4 sc = *(const uint4 *)(slot + rq[i]);
+          u32 hd = dg, e = E[i], h;
+          dg = H[i];
+          swb_cell<MODE>(hd, sc.x, e, f0, h, smax, negq, negr); hd = hup0; hup0 = h;
+          swb_cell<MODE>(hd, sc.y, e, f1, h, smax, negq, negr); hd = hup1; hup1 = h;
+          swb_cell<MODE>(hd, sc.z, e, f2, h, smax, negq, negr); hd = hup2; hup2 = h;
+          swb_cell<MODE>(hd, sc.w, e, f3, h, smax, negq, negr); hup3 = h;
+          H[i] = h;
+          E[i] = e;
+        }
+        dtop = ih3;
+        if (spill)
+        {
+          P.bndH[b0 + b] = make_uint4(hup0, hup1, hup2, hup3);
+          P.bndF[b0 + b] = make_uint4(f0, f1, f2, f3);
+        }
+        if (g == G - 1 && (flags & SWB_FLAG_END))
+        {
+          u32 v = smax;
+          if (pass > 0) v = __vmaxs2(v, P.pair_scores[pair_out]);
+          P.pair_scores[pair_out] = v;
+          pair_out++;
+        }
+      }
+
+      // ---- hand the strip's bottom row to the next thread of the group ------------------------
+      ih0 = __shfl_up_sync(0xffffffffu, hup0, 1, G);
+      ih1 = __shfl_up_sync(0xffffffffu, hup1, 1, G);
+      ih2 = __shfl_up_sync(0xffffffffu, hup2, 1, G);
+      ih3 = __shfl_up_sync(0xffffffffu, hup3, 1, G);
+      if0 = __shfl_up_sync(0xffffffffu, f0, 1, G);
+      if1 = __shfl_up_sync(0xffffffffu, f1, 1, G);
+      if2 = __shfl_up_sync(0xffffffffu, f2, 1, G);
+      if3 = __shfl_up_sync(0xffffffffu, f3, 1, G);
+      is = __shfl_up_sync(0xffffffffu, smax, 1, G);
+      if (g == 0) { ih0 = ih1 = ih2 = ih3 = 0; if0 = if1 = if2 = if3 = 0; is = 0; }
+      cur = nxt;
+      __syncwarp();
+    }
+  }
+}
+
+// ---- wide kernel: one thread per subject, 32- or 64-bit cells ------------------------------
+// Used for subjects whose 16-bit lane reached the overflow limit, for scoring systems the
+// packed kernel cannot represent, and (with END = true) for search16s's alignment-end contract
+// (search16s.cc:390-405): first column reaching the final maximum, smallest row within it.
+// H/E of the query rows live in a global scratch laid out [row][thread] so a warp's accesses
+// coalesce.
+struct WideParams
+{
+  const unsigned char *residues;   // raw database symbols as uploaded
+  const long long *offsets;        // [nseq+1]
+  int trailing;
+  const long long *list;           // caller's list of subject numbers, or NULL (position = subject)
+  const long long *sel;            // positions of that list to score, or NULL (all of them)
+  long long nsel;
+  const unsigned char *query;
+  int qlen;
+  const long long *matrix;         // [32][32] (subject << 5) + query
+  long long q, r;
+  void *he;                        // [2*qlen][stride] of T
+  long long stride;
+  long long *scores;               // indexed by list position
+  long long *bestpos, *bestq;      // END only, indexed like scores
+};
+
+template <typename T, bool END>
+__global__ void __launch_bounds__(128) swb_wide_kernel(const WideParams P)
+{
+  __shared__ T Msh[32 * 32];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) Msh[i] = (T)P.matrix[i];
+  __syncthreads();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= P.nsel) return;
+  const long long item = P.sel ? P.sel[tid] : tid;
+  const long long subj = P.list ? (P.list[item] >> 3) : item;
+  const long long o0 = P.offsets[subj];
+  const long long dlen = P.offsets[subj + 1] - o0 - P.trailing;
+  const unsigned char *d = P.residues + o0;
+  T *he = (T *)P.he + tid;
+  const long long st = P.stride;
+  const int qlen = P.qlen;
+  const T q = (T)P.q, r = (T)P.r;
+  for (int i = 0; i < 2 * qlen; i++) he[i * st] = 0;
+  T best = 0;
+  long long bq = -1, bd = -1;
+  for (long long j = 0; j < dlen; j++)
+  {
+    const T *row = Msh + ((d[j] & 31) << 5);
+    T f = 0, h = 0;
+    for (int i = 0; i < qlen; i++)
+    {
+      const T hn = he[(2 * i) * st];
+      T e = he[(2 * i + 1) * st];
+      h += row[P.query[i]];
+      h = h > e ? h : e;
+      h = h > f ? h : f;
+      h = h > 0 ? h : 0;
+      if (h > best) { best = h; if (END) { bq = i; bd = j; } }
+      he[(2 * i) * st] = h;
+      const T hq = h - q;
+      e -= r; f -= r;
+      e = e > hq ? e : hq;
+      f = f > hq ? f : hq;
+      he[(2 * i + 1) * st] = e;
+      h = hn;
+    }
+  }
+  P.scores[item] = (long long)best;
+  if (END) { P.bestpos[item] = bd; P.bestq[item] = bq; }
+}
+
+// ---- layout kernels ------------------------------------------------------------------------------
+// keys for the length sort: subject k of the list -> its length
+__global__ void swb_len_kernel(const long long *offsets, int trailing, const long long *list,
+                               long long n, u32 *keys, u32 *vals)
+{
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const long long s = list ? (list[k] >> 3) : k;
+  long long len = offsets[s + 1] - offsets[s] - trailing;
+  if (len < 0) len = 0;
+  keys[k] = (u32)len;
+  vals[k] = (u32)k;
+}
+
+// blocks per pair from the sorted lengths (descending): pair p = sorted entries 2p, 2p+1
+__global__ void swb_pairblk_kernel(const u32 *sorted_len, long long n, long long npairs,
+                                   long long *nblk)
+{
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const u32 la = sorted_len[2 * p];           // descending: the first of the pair is the longer
+  nblk[p] = (la + 3) / 4;
+}
+
+// one warp per pair: interleave the two subjects into 8-byte blocks
+__global__ void swb_fill_kernel(const unsigned char *residues, const long long *offsets,
+                                int trailing, const long long *list, const u32 *sorted_len,
+                                const u32 *sorted_idx, long long n, long long npairs,
+                                const long long *pairblk, uint2 *blocks)
+{
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= npairs) return;
+  const long long nb = pairblk[p + 1] - pairblk[p];
+  if (nb == 0) return;
+  const u32 ka = sorted_idx[2 * p];
+  const long long sa = list ? (list[ka] >> 3) : (long long)ka;
+  const unsigned char *da = residues + offsets[sa];
+  const u32 la = sorted_len[2 * p];
+  const unsigned char *db = da;
+  u32 lb = 0;
+  if (2 * p + 1 < n)
+  {
+    const u32 kb = sorted_idx[2 * p + 1];
+    const long long sb = list ? (list[kb] >> 3) : (long long)kb;
+    db = residues + offsets[sb];
+    lb = sorted_len[2 * p + 1];
+  }
+  uint2 *out = blocks + pairblk[p];
+  for (long long b = lane; b < nb; b += 32)
+  {
+    u32 x = 0, y = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+    {
+      const long long j = b * 4 + c;
+      const u32 ra = j < la ? (u32)(da[j] & 31) : (u32)SWB_PAD_CODE;
+      const u32 rb = j < lb ? (u32)(db[j] & 31) : (u32)SWB_PAD_CODE;
+      x |= ra << (8 * c);
+      y |= rb << (8 * c);
+    }
+    u32 flags = 0;
+    if (b == 0) flags |= SWB_FLAG_START;
+    if (b == nb - 1) flags |= SWB_FLAG_END;
+    x |= flags << 6;
+    out[b] = make_uint2(x, y);
+  }
+}
+
+// stream s covers pairs [stream_pair[s], stream_pair[s+1]): equal shares of the block total
+__global__ void swb_partition_kernel(const long long *pairblk, long long npairs, int nstreams,
+                                     int *stream_pair)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nstreams) return;
+  if (s == nstreams) { stream_pair[s] = (int)npairs; return; }
+  const long long total = pairblk[npairs];
+  const long long target = (long long)(((__int128)total * s) / nstreams);
+  long long lo = 0, hi = npairs;                 // first p with pairblk[p] >= target
+  while (lo < hi)
+  {
+    const long long mid = (lo + hi) >> 1;
+    if (pairblk[mid] >= target) hi = mid; else lo = mid + 1;
+  }
+  stream_pair[s] = (int)lo;
+}
+
+// unpack lane maxima into per-subject scores; lanes at or above the limit are queued for the
+// wide kernel instead (the reference's re-queue, swipe.cc:1459-1479, :1514-1537)
+__global__ void swb_finish_kernel(const u32 *pair_scores, const u32 *sorted_idx, long long n,
+                                  int limit, long long *scores, long long *requeue,
+                                  unsigned long long *nrequeue)
+{
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const u32 w = pair_scores[k >> 1];
+  const int v = (int)((k & 1) ? (w >> 16) : (w & 0xffffu));
+  const u32 pos = sorted_idx[k];                 // position in the caller's list
+  if (v >= limit)
+  {
+    const unsigned long long slot = atomicAdd(nrequeue, 1ull);
+    requeue[slot] = (long long)pos;
+  }
+  else
+    scores[pos] = v;
+}
+
+// reference-width bookkeeping: which of the reference's passes would have kept each score
+__global__ void swb_widthcount_kernel(const long long *scores, long long n, long long limit7,
+                                      long long limit16, unsigned long long *counts)
+{
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int w = -1;
+  if (k < n)
+  {
+    const long long v = scores[k];
+    w = v < limit7 ? 0 : (v < limit16 ? 1 : 2);
+  }
+  for (int c = 0; c < 3; c++)
+  {
+    const unsigned m = __ballot_sync(0xffffffffu, w == c);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counts[c], (unsigned long long)__popc(m));
+  }
+}

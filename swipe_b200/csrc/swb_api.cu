@@ -1,0 +1,794 @@
+// swb_api.cu -- the C ABI of include/swipe_b200.h: database shard upload and device-side
+// re-layout, the scoring-table setup, the width cascade and the top-K sink.
+//
+// Host-side roles taken over from the reference (torognes/swipe):
+//   search_chunk's cascade ............ swipe.cc:1416-1594   -> swb_search / swb_search_list
+//   db_mapsequences / db_getsequence .. database.cc:1082-1131, :1237-1401 -> swb_db_open
+//   score limits ...................... matrices.cc:560-577  -> Tables::prepare
+//   hits_enter ........................ hits.cc:163-222      -> swb_topk_merge
+#include "../../include/swipe_b200.h"
+#include "sw_kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace
+{
+
+thread_local std::string g_cuda_error;
+
+#define SWB_CUDA(call)                                                                        \
+  do                                                                                          \
+  {                                                                                           \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+    {                                                                                         \
+      char buf_[512];                                                                         \
+      snprintf(buf_, sizeof buf_, "%s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__,       \
+               __LINE__, #call);                                                              \
+      g_cuda_error = buf_;                                                                    \
+      (void)cudaGetLastError();                                                               \
+      return e_ == cudaErrorMemoryAllocation ? SWB_ERR_NOMEM : SWB_ERR_CUDA;                  \
+    }                                                                                         \
+  } while (0)
+
+#define SWB_TRY(expr)                 \
+  do                                  \
+  {                                   \
+    int rc_ = (expr);                 \
+    if (rc_ != SWB_OK) return rc_;    \
+  } while (0)
+
+template <typename T> struct DevBuf
+{
+  T *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n)
+  {
+    if (n <= cap && p) return SWB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n ? n : 1;
+    SWB_CUDA(cudaMalloc((void **)&p, want * sizeof(T)));
+    cap = want;
+    return SWB_OK;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// The device-resident form of a set of subjects: length-sorted (descending), paired, cut
+// into 4-column blocks.  Built for the whole shard at open time and for ad-hoc lists.
+struct Layout
+{
+  long long n = 0;        // subjects
+  long long npairs = 0;
+  long long cap_blocks = 0;
+  DevBuf<u32> keys_in, keys_out, idx_in, idx_out;   // idx_out[k] = list position of k-th longest
+  DevBuf<long long> nblk, pairblk;                  // [npairs+1]
+  DevBuf<uint2> blocks;
+  DevBuf<unsigned char> cub_tmp;
+  DevBuf<u32> pair_scores;
+  DevBuf<int> stream_pair;
+  int stream_pair_n = -1;                           // streams the partition was computed for
+  void release()
+  {
+    keys_in.release(); keys_out.release(); idx_in.release(); idx_out.release();
+    nblk.release(); pairblk.release(); blocks.release(); cub_tmp.release();
+    pair_scores.release(); stream_pair.release();
+  }
+};
+
+struct Shape { int G, R; };
+
+}  // namespace
+
+struct swb_db
+{
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  long long nseq = 0, total_res = 0, longest = 0;
+  int trailing = 0;
+  int mode = 0;
+  DevBuf<unsigned char> residues;
+  DevBuf<long long> offsets;
+  Layout all;      // the whole shard
+  Layout tmp;      // ad-hoc list layouts
+  // per-search device scratch
+  DevBuf<short> m16;
+  DevBuf<unsigned short> qrow_off;
+  DevBuf<long long> matrix;
+  DevBuf<unsigned char> query;
+  DevBuf<long long> scores, bestpos, bestq, requeue, list;
+  DevBuf<unsigned long long> counters;       // [0] requeue count, [1..3] width counts
+  DevBuf<unsigned char> he;
+  DevBuf<uint4> bndH, bndF;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double upload_ms = 0, layout_ms = 0;
+  int force_G = 0, force_R = 0, force_mode = -1;   // test hooks (swb_set_shape)
+};
+
+namespace
+{
+
+int build_layout(swb_db *db, Layout &L, const long long *d_list, long long n)
+{
+  cudaStream_t st = db->stream;
+  L.n = n;
+  L.npairs = (n + 1) / 2;
+  L.stream_pair_n = -1;
+  if (n == 0) return SWB_OK;
+  if (n > 0x7fffffffLL) return SWB_ERR_ARG;
+  SWB_TRY(L.keys_in.reserve(n)); SWB_TRY(L.keys_out.reserve(n + 1));
+  SWB_TRY(L.idx_in.reserve(n)); SWB_TRY(L.idx_out.reserve(n + 1));
+  SWB_TRY(L.nblk.reserve(L.npairs + 1)); SWB_TRY(L.pairblk.reserve(L.npairs + 1));
+  SWB_TRY(L.pair_scores.reserve(L.npairs));
+  const int T = 256;
+  swb_len_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(db->offsets.p, db->trailing, d_list, n,
+                                                            L.keys_in.p, L.idx_in.p);
+  SWB_CUDA(cudaGetLastError());
+  size_t tmp1 = 0, tmp2 = 0;
+  int bits = 1;
+  while (bits < 32 && (db->longest >> bits) != 0) bits++;
+  SWB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp1, L.keys_in.p, L.keys_out.p,
+                                                     L.idx_in.p, L.idx_out.p, (int)n, 0, bits, st));
+  SWB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, L.nblk.p, L.pairblk.p,
+                                         (int)(L.npairs + 1), st));
+  SWB_TRY(L.cub_tmp.reserve(std::max(tmp1, tmp2)));
+  size_t tb = L.cub_tmp.cap;
+  SWB_CUDA(cub::DeviceRadixSort::SortPairsDescending(L.cub_tmp.p, tb, L.keys_in.p, L.keys_out.p,
+                                                     L.idx_in.p, L.idx_out.p, (int)n, 0, bits, st));
+  // an odd subject count leaves the last pair's second lane empty
+  SWB_CUDA(cudaMemsetAsync(L.keys_out.p + n, 0, sizeof(u32), st));
+  SWB_CUDA(cudaMemsetAsync(L.nblk.p + L.npairs, 0, sizeof(long long), st));
+  swb_pairblk_kernel<<<(unsigned)((L.npairs + T - 1) / T), T, 0, st>>>(L.keys_out.p, n, L.npairs,
+                                                                      L.nblk.p);
+  SWB_CUDA(cudaGetLastError());
+  tb = L.cub_tmp.cap;
+  SWB_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp.p, tb, L.nblk.p, L.pairblk.p,
+                                         (int)(L.npairs + 1), st));
+  // upper bound of the block total without a round trip: sum(max len) <= total residues
+  long long bound_res = d_list ? 0 : db->total_res;
+  if (d_list) bound_res = std::min<long long>(db->total_res, n * db->longest);
+  L.cap_blocks = (bound_res + 3 * L.npairs) / 4 + 1;
+  SWB_TRY(L.blocks.reserve((size_t)L.cap_blocks));
+  const long long threads = L.npairs * 32;
+  swb_fill_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(
+      db->residues.p, db->offsets.p, db->trailing, d_list, L.keys_out.p, L.idx_out.p, n, L.npairs,
+      L.pairblk.p, L.blocks.p);
+  SWB_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
+
+// ---- scoring tables ------------------------------------------------------------------------
+struct Tables
+{
+  int nq = 0;                  // distinct query symbols = table rows
+  int rowof[32];               // query symbol -> table row
+  long long hi = 0, lo = 0;    // over the whole 32x32 table (matrices.cc:560-571)
+  long long limit7 = 0, limit16 = 0;
+  bool narrow_ok = false;      // the packed kernels can represent this scoring system
+  bool hybrid_ok = false;
+  std::vector<short> m16;      // [33][32]
+  std::vector<unsigned short> qrow;
+};
+
+inline short enc16(long long v, int mode)
+{
+  if (mode == SWB_MODE_HYBRID && v < 0) return (short)(0x8000u | (unsigned)(-v));
+  return (short)v;
+}
+
+int prepare_tables(Tables &t, const unsigned char *query, long long qlen, const swb_scoring *sc,
+                   int mode, int rows_padded)
+{
+  for (int i = 0; i < 32; i++) t.rowof[i] = -1;
+  t.nq = 0;
+  for (long long i = 0; i < qlen; i++)
+  {
+    if (query[i] > 31) return SWB_ERR_ARG;
+    if (t.rowof[query[i]] < 0) t.rowof[query[i]] = t.nq++;
+  }
+  t.hi = -100; t.lo = 100;
+  for (int i = 0; i < 1024; i++)
+  {
+    t.hi = std::max(t.hi, (long long)sc->matrix[i]);
+    t.lo = std::min(t.lo, (long long)sc->matrix[i]);
+  }
+  t.limit7 = 128 - t.hi;
+  t.limit16 = 65536 - t.hi;
+  const long long q = sc->gap_open_extend, r = sc->gap_extend;
+  t.narrow_ok = t.nq <= 30 && t.hi <= 1024 && t.lo >= -1024 && q >= 0 && q <= 8192 && r >= 0 &&
+                r <= 8192;
+  t.hybrid_ok = t.narrow_ok && t.hi <= 256 && t.lo >= -1023 && q <= 1023 && r <= 1023;
+  t.m16.assign(SWB_MROWS * 32, 0);
+  for (int d = 0; d < SWB_MROWS; d++)
+    for (int s = 0; s < 32; s++)
+    {
+      long long v = SWB_PAD_SCORE;
+      if (d < 32)
+        for (int qs = 0; qs < 32; qs++)
+          if (t.rowof[qs] == s) v = sc->matrix[(d << 5) + qs];
+      t.m16[d * 32 + s] = t.narrow_ok ? enc16(v, mode) : (short)0;
+    }
+  t.qrow.assign((size_t)rows_padded, (unsigned short)((t.nq + 1) * 16));
+  for (long long i = 0; i < qlen && i < rows_padded; i++)
+    t.qrow[(size_t)i] = (unsigned short)(t.rowof[query[i]] * 16);
+  return SWB_OK;
+}
+
+// ---- kernel shapes -----------------------------------------------------------------------------
+typedef void (*scan_fn)(const ScanParams);
+struct ShapeEntry { int G, R, mode; scan_fn fn; };
+
+#define SWB_SHAPE(G, R)                                           \
+  {G, R, SWB_MODE_INT16, swb_scan_kernel<G, R, SWB_MODE_INT16>},  \
+  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID>}
+
+const ShapeEntry g_shapes[] = {
+    SWB_SHAPE(8, 8),   SWB_SHAPE(8, 13),  SWB_SHAPE(8, 16),  SWB_SHAPE(16, 12), SWB_SHAPE(16, 16),
+    SWB_SHAPE(16, 20), SWB_SHAPE(16, 24), SWB_SHAPE(32, 12), SWB_SHAPE(32, 16), SWB_SHAPE(32, 20),
+    SWB_SHAPE(32, 24), SWB_SHAPE(32, 28), SWB_SHAPE(32, 32),
+};
+const int g_nshapes = (int)(sizeof(g_shapes) / sizeof(g_shapes[0]));
+
+// rows covered per pass = G*R; cost ~ padded rows * (1 + per-step overhead / R)
+const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, int *npass)
+{
+  const ShapeEntry *best = nullptr;
+  double best_cost = 0;
+  for (int i = 0; i < g_nshapes; i++)
+  {
+    const ShapeEntry &s = g_shapes[i];
+    if (s.mode != mode) continue;
+    if (db->force_G && (s.G != db->force_G || s.R != db->force_R)) continue;
+    const long long rows = (long long)s.G * s.R;
+    const long long np = std::max<long long>(1, (qlen + rows - 1) / rows);
+    const double cost = (double)(np * rows) * (1.0 + 2.5 / s.R) * (np > 1 ? 1.02 : 1.0);
+    if (!best || cost < best_cost) { best = &s; best_cost = cost; *npass = (int)np; }
+  }
+  return best;
+}
+
+int run_wide(swb_db *db, const long long *d_list, const long long *d_sel, long long nsel,
+             const unsigned char *d_query, long long qlen, const swb_scoring *sc, bool end,
+             bool use64, int *launches)
+{
+  if (nsel == 0) return SWB_OK;
+  cudaStream_t st = db->stream;
+  const long long batch = 1 << 16;
+  const size_t cell = use64 ? 8 : 4;
+  SWB_TRY(db->he.reserve((size_t)(2 * std::max<long long>(qlen, 1)) *
+                         (size_t)std::min(batch, nsel) * cell));
+  for (long long first = 0; first < nsel; first += batch)
+  {
+    const long long m = std::min(batch, nsel - first);
+    WideParams W;
+    W.residues = db->residues.p; W.offsets = db->offsets.p; W.trailing = db->trailing;
+    W.list = d_list; W.sel = d_sel ? d_sel + first : nullptr; W.nsel = m;
+    W.query = d_query; W.qlen = (int)qlen; W.matrix = db->matrix.p;
+    W.q = sc->gap_open_extend; W.r = sc->gap_extend;
+    W.he = db->he.p; W.stride = m;
+    W.scores = db->scores.p; W.bestpos = db->bestpos.p; W.bestq = db->bestq.p;
+    if (!d_sel)
+    {
+      // dense positions first .. first+m-1: shift the output views instead of building a list
+      W.scores += first; W.bestpos = W.bestpos ? W.bestpos + first : nullptr;
+      W.bestq = W.bestq ? W.bestq + first : nullptr;
+      W.list = d_list ? d_list + first : nullptr;
+      if (!d_list) { W.offsets += first; }
+    }
+    const unsigned grid = (unsigned)((m + 127) / 128);
+    if (use64)
+    {
+      if (end) swb_wide_kernel<long long, true><<<grid, 128, 0, st>>>(W);
+      else swb_wide_kernel<long long, false><<<grid, 128, 0, st>>>(W);
+    }
+    else
+    {
+      if (end) swb_wide_kernel<int, true><<<grid, 128, 0, st>>>(W);
+      else swb_wide_kernel<int, false><<<grid, 128, 0, st>>>(W);
+    }
+    SWB_CUDA(cudaGetLastError());
+    (*launches)++;
+  }
+  return SWB_OK;
+}
+
+int check_args(const swb_db *db, const unsigned char *query, long long qlen, const swb_scoring *sc)
+{
+  if (!db || !sc || !sc->matrix || qlen < 0 || (qlen > 0 && !query)) return SWB_ERR_ARG;
+  if (qlen > 0x3fffffff) return SWB_ERR_ARG;
+  if (sc->gap_open_extend < 0 || sc->gap_extend < 0) return SWB_ERR_ARG;
+  return SWB_OK;
+}
+
+// The cascade over n subjects (the whole shard when h_list == NULL).
+int search_impl(swb_db *db, const unsigned char *query, long long qlen, const swb_scoring *sc,
+                const long long *h_list, long long n, long long *scores, long long *bestpos,
+                long long *bestq, swb_counters *ctr)
+{
+  SWB_TRY(check_args(db, query, qlen, sc));
+  if (n < 0 || (n > 0 && !scores)) return SWB_ERR_ARG;
+  SWB_CUDA(cudaSetDevice(db->device));
+  cudaStream_t st = db->stream;
+  const bool want_end = bestpos != nullptr;
+  swb_counters c;
+  memset(&c, 0, sizeof c);
+  c.subjects = n;
+  int launches = 0;
+
+  if (h_list)
+    for (long long k = 0; k < n; k++)
+    {
+      if ((h_list[k] & 7) != 0) return SWB_ERR_ARG;           // strand / frame must be 0
+      const long long s = h_list[k] >> 3;
+      if (s < 0 || s >= db->nseq) return SWB_ERR_ARG;
+    }
+
+  // scoring tables; the score range decides whether the wide kernel needs 64-bit cells
+  int mode = SWB_MODE_HYBRID;
+  if (db->force_mode >= 0) mode = db->force_mode;
+  Tables tb;
+  int npass = 1;
+  {
+    Tables probe;
+    SWB_TRY(prepare_tables(probe, query, qlen, sc, mode, 0));
+    if (mode == SWB_MODE_HYBRID && !probe.hybrid_ok) mode = SWB_MODE_INT16;
+  }
+  const ShapeEntry *shape = choose_shape(db, qlen, mode, &npass);
+  if (!shape) return SWB_ERR_INTERNAL;
+  const long long rows_padded = (long long)npass * shape->G * shape->R;
+  SWB_TRY(prepare_tables(tb, query, qlen, sc, mode, (int)rows_padded));
+  const long long maxcell = std::max<long long>(tb.hi, 0) * std::min<long long>(qlen, db->longest);
+  const bool use64 = maxcell + sc->gap_open_extend + 65536 > 0x7fffffffLL ||
+                     sc->gap_open_extend > 0x3fffffff || tb.lo < -0x3fffffff;
+
+  SWB_TRY(db->scores.reserve((size_t)std::max<long long>(n, 1)));
+  SWB_TRY(db->counters.reserve(8));
+  SWB_TRY(db->matrix.reserve(1024));
+  SWB_TRY(db->query.reserve((size_t)std::max<long long>(qlen, 1)));
+  SWB_CUDA(cudaMemcpyAsync(db->matrix.p, sc->matrix, 1024 * sizeof(long long),
+                           cudaMemcpyHostToDevice, st));
+  if (qlen > 0)
+    SWB_CUDA(cudaMemcpyAsync(db->query.p, query, (size_t)qlen, cudaMemcpyHostToDevice, st));
+  SWB_CUDA(cudaMemsetAsync(db->counters.p, 0, 8 * sizeof(unsigned long long), st));
+  if (want_end)
+  {
+    SWB_TRY(db->bestpos.reserve((size_t)std::max<long long>(n, 1)));
+    SWB_TRY(db->bestq.reserve((size_t)std::max<long long>(n, 1)));
+  }
+  const long long *d_list = nullptr;
+  if (h_list && n > 0)
+  {
+    SWB_TRY(db->list.reserve((size_t)n));
+    SWB_CUDA(cudaMemcpyAsync(db->list.p, h_list, (size_t)n * sizeof(long long),
+                             cudaMemcpyHostToDevice, st));
+    d_list = db->list.p;
+  }
+
+  long long nrequeue = 0;
+  const bool narrow = !want_end && db->mode == 0 && tb.narrow_ok && qlen > 0 && n > 0;
+  if (n == 0)
+  {
+  }
+  else if (qlen == 0)
+  {
+    SWB_CUDA(cudaMemsetAsync(db->scores.p, 0, (size_t)n * sizeof(long long), st));
+  }
+  else if (narrow)
+  {
+    Layout *L = &db->all;
+    if (d_list)
+    {
+      L = &db->tmp;
+      SWB_TRY(build_layout(db, *L, d_list, n));
+      launches += 5;
+    }
+    // launch geometry: 4 warps per CTA, as many CTAs per SM as shared memory and registers allow
+    const int slot_bytes = (tb.nq + 2) * 16;
+    const size_t smem = SWB_SMEM_HEADER + (size_t)4 * 32 * slot_bytes;
+    SWB_CUDA(cudaFuncSetAttribute((const void *)shape->fn,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)shape->fn, 128, smem));
+    if (occ < 1) return SWB_ERR_INTERNAL;
+    const int grid = db->sm_count * occ;
+    const int nstreams = grid * 4 * (32 / shape->G);
+    if (L->stream_pair_n != nstreams)
+    {
+      SWB_TRY(L->stream_pair.reserve((size_t)nstreams + 1));
+      swb_partition_kernel<<<(nstreams + 1 + 255) / 256, 256, 0, st>>>(L->pairblk.p, L->npairs,
+                                                                       nstreams, L->stream_pair.p);
+      SWB_CUDA(cudaGetLastError());
+      launches++;
+      L->stream_pair_n = nstreams;
+    }
+    SWB_TRY(db->m16.reserve(SWB_MROWS * 32));
+    SWB_TRY(db->qrow_off.reserve((size_t)rows_padded));
+    SWB_CUDA(cudaMemcpyAsync(db->m16.p, tb.m16.data(), tb.m16.size() * sizeof(short),
+                             cudaMemcpyHostToDevice, st));
+    SWB_CUDA(cudaMemcpyAsync(db->qrow_off.p, tb.qrow.data(), tb.qrow.size() * sizeof(unsigned short),
+                             cudaMemcpyHostToDevice, st));
+    if (npass > 1)
+    {
+      SWB_TRY(db->bndH.reserve((size_t)L->cap_blocks));
+      SWB_TRY(db->bndF.reserve((size_t)L->cap_blocks));
+    }
+    SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * sizeof(u32), st));
+    ScanParams P;
+    P.blocks = L->blocks.p; P.pairblk = L->pairblk.p; P.stream_pair = L->stream_pair.p;
+    P.pair_scores = L->pair_scores.p; P.m16 = db->m16.p; P.qrow_off = db->qrow_off.p;
+    P.bndH = db->bndH.p; P.bndF = db->bndF.p;
+    P.nq = tb.nq; P.slot_bytes = slot_bytes; P.npass = npass;
+    const long long q = sc->gap_open_extend, r = sc->gap_extend;
+    const unsigned nq16 = (unsigned)(unsigned short)enc16(-q, mode);
+    const unsigned nr16 = (unsigned)(unsigned short)(short)(-r);
+    const unsigned pad16 = (unsigned)(unsigned short)enc16(SWB_PAD_SCORE, mode);
+    P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
+    const int limit = (mode == SWB_MODE_HYBRID ? 2047 : 32767) - (int)std::max<long long>(tb.hi, 0);
+    SWB_CUDA(cudaEventRecord(db->ev[0], st));
+    shape->fn<<<grid, 128, smem, st>>>(P);
+    SWB_CUDA(cudaGetLastError());
+    SWB_CUDA(cudaEventRecord(db->ev[1], st));
+    launches++;
+    SWB_TRY(db->requeue.reserve((size_t)n));
+    swb_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        L->pair_scores.p, L->idx_out.p, n, limit, db->scores.p, db->requeue.p, db->counters.p);
+    SWB_CUDA(cudaGetLastError());
+    launches++;
+    unsigned long long h_nreq = 0;
+    SWB_CUDA(cudaMemcpyAsync(&h_nreq, db->counters.p, sizeof h_nreq, cudaMemcpyDeviceToHost, st));
+    SWB_CUDA(cudaStreamSynchronize(st));
+    nrequeue = (long long)h_nreq;
+    SWB_CUDA(cudaEventRecord(db->ev[2], st));
+    SWB_TRY(run_wide(db, d_list, db->requeue.p, nrequeue, db->query.p, qlen, sc, false, use64,
+                     &launches));
+    SWB_CUDA(cudaEventRecord(db->ev[3], st));
+  }
+  else
+  {
+    SWB_CUDA(cudaEventRecord(db->ev[0], st));
+    SWB_CUDA(cudaEventRecord(db->ev[1], st));
+    SWB_CUDA(cudaEventRecord(db->ev[2], st));
+    SWB_TRY(run_wide(db, d_list, nullptr, n, db->query.p, qlen, sc, want_end, use64, &launches));
+    SWB_CUDA(cudaEventRecord(db->ev[3], st));
+    nrequeue = n;
+  }
+
+  if (n > 0)
+  {
+    swb_widthcount_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        db->scores.p, n, tb.limit7, tb.limit16, db->counters.p + 1);
+    SWB_CUDA(cudaGetLastError());
+    launches++;
+    unsigned long long h_cnt[4] = {0, 0, 0, 0};
+    SWB_CUDA(cudaMemcpyAsync(scores, db->scores.p, (size_t)n * sizeof(long long),
+                             cudaMemcpyDeviceToHost, st));
+    if (want_end)
+    {
+      SWB_CUDA(cudaMemcpyAsync(bestpos, db->bestpos.p, (size_t)n * sizeof(long long),
+                               cudaMemcpyDeviceToHost, st));
+      SWB_CUDA(cudaMemcpyAsync(bestq, db->bestq.p, (size_t)n * sizeof(long long),
+                               cudaMemcpyDeviceToHost, st));
+    }
+    SWB_CUDA(cudaMemcpyAsync(h_cnt, db->counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+    SWB_CUDA(cudaStreamSynchronize(st));
+    c.ref_width7 = (long long)h_cnt[1];
+    c.ref_width16 = (long long)h_cnt[2];
+    c.ref_width63 = (long long)h_cnt[3];
+    if (qlen > 0)
+    {
+      float ms = 0;
+      SWB_CUDA(cudaEventElapsedTime(&ms, db->ev[0], db->ev[1]));
+      c.scan_ms = ms;
+      SWB_CUDA(cudaEventElapsedTime(&ms, db->ev[2], db->ev[3]));
+      c.requeue_ms = ms;
+    }
+  }
+  c.gpu_requeued = nrequeue;
+  c.gpu_narrow = n - nrequeue;
+  c.kernel_launches = launches;
+  // cells: the reference's GCUPS numerator, symbols * qlen (swipe.cc:1744-1775)
+  if (!h_list) c.cells = db->total_res * qlen;
+  if (ctr) *ctr = c;
+  return SWB_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int swb_abi_version(void) { return SWB_ABI_VERSION; }
+
+const char *swb_strerror(int status)
+{
+  switch (status)
+  {
+    case SWB_OK: return "ok";
+    case SWB_ERR_ARG: return "invalid argument";
+    case SWB_ERR_NO_DEVICE: return "no usable CUDA device (an sm_100 GPU is required; there is no CPU path)";
+    case SWB_ERR_CUDA: return "CUDA runtime error";
+    case SWB_ERR_NOMEM: return "out of device or host memory";
+    case SWB_ERR_RANGE: return "scoring parameters out of range";
+    case SWB_ERR_INTERNAL: return "internal error";
+    default: return "unknown status";
+  }
+}
+
+const char *swb_last_cuda_error(void) { return g_cuda_error.c_str(); }
+
+int swb_device_count(int *count)
+{
+  if (!count) return SWB_ERR_ARG;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+  {
+    g_cuda_error = cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    *count = 0;
+    return SWB_ERR_NO_DEVICE;
+  }
+  *count = n;
+  return SWB_OK;
+}
+
+int swb_host_alloc(void **ptr, int64_t bytes)
+{
+  if (!ptr || bytes < 0) return SWB_ERR_ARG;
+  SWB_CUDA(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+  return SWB_OK;
+}
+
+int swb_host_free(void *ptr)
+{
+  if (ptr) SWB_CUDA(cudaFreeHost(ptr));
+  return SWB_OK;
+}
+
+int swb_db_open(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
+                int trailing, void *stream, swb_db **out)
+{
+  if (!out) return SWB_ERR_ARG;
+  *out = nullptr;
+  if (nseq < 0 || !offsets || trailing < 0 || trailing > 1 || nseq > 0x7ffffff0LL) return SWB_ERR_ARG;
+  const long long span = offsets[nseq] - offsets[0];
+  if (span < 0 || (span > 0 && !residues)) return SWB_ERR_ARG;
+  long long total = 0, longest = 0;
+  for (long long i = 0; i < nseq; i++)
+  {
+    const long long len = offsets[i + 1] - offsets[i] - trailing;
+    if (len < 0 || len > 0x7fffffffLL) return SWB_ERR_ARG;
+    total += len;
+    longest = std::max(longest, len);
+  }
+  int ndev = 0;
+  SWB_TRY(swb_device_count(&ndev));
+  if (device < 0 || device >= ndev) return SWB_ERR_NO_DEVICE;
+  SWB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SWB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+  {
+    g_cuda_error = std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                   ", the kernels are built for sm_100a only";
+    return SWB_ERR_NO_DEVICE;
+  }
+  swb_db *db = new (std::nothrow) swb_db;
+  if (!db) return SWB_ERR_NOMEM;
+  db->device = device;
+  db->sm_count = prop.multiProcessorCount;
+  db->nseq = nseq; db->total_res = total; db->longest = longest; db->trailing = trailing;
+  int rc = SWB_OK;
+  do
+  {
+#define SWB_STEP(x) if ((rc = (x)) != SWB_OK) break
+    if (stream) db->stream = (cudaStream_t)stream;
+    else
+    {
+      SWB_STEP([&]() -> int { SWB_CUDA(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking)); return SWB_OK; }());
+      db->own_stream = true;
+    }
+    SWB_STEP([&]() -> int {
+      for (int i = 0; i < 4; i++) SWB_CUDA(cudaEventCreate(&db->ev[i]));
+      return SWB_OK;
+    }());
+    SWB_STEP(db->residues.reserve((size_t)span + 16));
+    SWB_STEP(db->offsets.reserve((size_t)nseq + 1));
+    SWB_STEP([&]() -> int {
+      cudaStream_t st = db->stream;
+      SWB_CUDA(cudaEventRecord(db->ev[0], st));
+      // offsets are rebased so that residues[0] is the first byte uploaded
+      std::vector<long long> rebased;
+      const long long *src = (const long long *)offsets;
+      if (offsets[0] != 0)
+      {
+        rebased.resize((size_t)nseq + 1);
+        for (long long i = 0; i <= nseq; i++) rebased[(size_t)i] = offsets[i] - offsets[0];
+        src = rebased.data();
+      }
+      SWB_CUDA(cudaMemcpyAsync(db->offsets.p, src, ((size_t)nseq + 1) * sizeof(long long),
+                               cudaMemcpyHostToDevice, st));
+      if (span > 0)
+        SWB_CUDA(cudaMemcpyAsync(db->residues.p, residues + offsets[0], (size_t)span,
+                                 cudaMemcpyHostToDevice, st));
+      SWB_CUDA(cudaStreamSynchronize(st));     // rebased may go out of scope
+      SWB_CUDA(cudaEventRecord(db->ev[1], st));
+      return SWB_OK;
+    }());
+    SWB_STEP(build_layout(db, db->all, nullptr, nseq));
+    SWB_STEP([&]() -> int {
+      cudaStream_t st = db->stream;
+      SWB_CUDA(cudaEventRecord(db->ev[2], st));
+      SWB_CUDA(cudaStreamSynchronize(st));
+      float ms = 0;
+      SWB_CUDA(cudaEventElapsedTime(&ms, db->ev[0], db->ev[1]));
+      db->upload_ms = ms;
+      SWB_CUDA(cudaEventElapsedTime(&ms, db->ev[1], db->ev[2]));
+      db->layout_ms = ms;
+      return SWB_OK;
+    }());
+#undef SWB_STEP
+  } while (0);
+  if (rc != SWB_OK)
+  {
+    swb_db_close(db);
+    return rc;
+  }
+  *out = db;
+  return SWB_OK;
+}
+
+int swb_db_close(swb_db *db)
+{
+  if (!db) return SWB_OK;
+  cudaSetDevice(db->device);
+  if (db->stream) cudaStreamSynchronize(db->stream);
+  db->residues.release(); db->offsets.release(); db->all.release(); db->tmp.release();
+  db->m16.release(); db->qrow_off.release(); db->matrix.release(); db->query.release();
+  db->scores.release(); db->bestpos.release(); db->bestq.release(); db->requeue.release();
+  db->list.release(); db->counters.release(); db->he.release(); db->bndH.release();
+  db->bndF.release();
+  for (int i = 0; i < 4; i++)
+    if (db->ev[i]) cudaEventDestroy(db->ev[i]);
+  if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
+  delete db;
+  (void)cudaGetLastError();
+  return SWB_OK;
+}
+
+int swb_db_info(const swb_db *db, int64_t *nseq, int64_t *total_residues, int64_t *longest)
+{
+  if (!db) return SWB_ERR_ARG;
+  if (nseq) *nseq = db->nseq;
+  if (total_residues) *total_residues = db->total_res;
+  if (longest) *longest = db->longest;
+  return SWB_OK;
+}
+
+int swb_search(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
+               int64_t *scores, swb_counters *counters)
+{
+  if (!db) return SWB_ERR_ARG;
+  return search_impl(db, query, qlen, scoring, nullptr, db->nseq, (long long *)scores, nullptr,
+                     nullptr, counters);
+}
+
+int swb_search_list(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
+                    const int64_t *seqnos, int64_t n, int64_t *scores, swb_counters *counters)
+{
+  if (!db || (n > 0 && !seqnos)) return SWB_ERR_ARG;
+  return search_impl(db, query, qlen, scoring, (const long long *)seqnos, n, (long long *)scores,
+                     nullptr, nullptr, counters);
+}
+
+int swb_search_end(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
+                   const int64_t *seqnos, int64_t n, int64_t *scores, int64_t *bestpos,
+                   int64_t *bestq)
+{
+  if (!db || (n > 0 && (!seqnos || !bestpos || !bestq))) return SWB_ERR_ARG;
+  long long dummy = 0;
+  return search_impl(db, query, qlen, scoring, (const long long *)seqnos, n, (long long *)scores,
+                     n > 0 ? (long long *)bestpos : &dummy, n > 0 ? (long long *)bestq : &dummy,
+                     nullptr);
+}
+
+int64_t swb_topk_merge(int nshards, const int64_t *const *scores, const int64_t *n,
+                       const int64_t *seqno_base, int64_t keep, int64_t min_score,
+                       int64_t upper_score, int64_t *out_seqno, int64_t *out_score,
+                       int64_t *totalhits, int64_t *obvious)
+{
+  if (nshards < 0 || keep < 0 || (nshards > 0 && (!scores || !n || !seqno_base))) return SWB_ERR_ARG;
+  if (keep > 0 && (!out_seqno || !out_score)) return SWB_ERR_ARG;
+  // hits_enter keeps (score desc, seqno desc) and, once full, only admits scores >= the last
+  // kept one; the final list therefore is the top `keep` of the admissible hits in that order,
+  // whatever the arrival order -- which is what makes the multi-GPU merge deterministic.
+  struct Hit { int64_t score, seqno; };
+  std::vector<Hit> heap;                       // min-heap on (score, seqno) of the best so far
+  auto worse = [](const Hit &a, const Hit &b) {
+    return a.score != b.score ? a.score > b.score : a.seqno > b.seqno;
+  };
+  int64_t tot = 0, obv = 0;
+  for (int s = 0; s < nshards; s++)
+  {
+    if (n[s] < 0 || (n[s] > 0 && !scores[s])) return SWB_ERR_ARG;
+    for (int64_t i = 0; i < n[s]; i++)
+    {
+      const int64_t sc = scores[s][i];
+      if (sc > upper_score) obv++;
+      if (sc >= min_score) tot++;
+      if (sc < min_score || sc > upper_score || keep == 0) continue;
+      const Hit h = {sc, seqno_base[s] + i};
+      if ((int64_t)heap.size() < keep)
+      {
+        heap.push_back(h);
+        std::push_heap(heap.begin(), heap.end(), worse);
+      }
+      else if (worse(h, heap.front()))
+      {
+        std::pop_heap(heap.begin(), heap.end(), worse);
+        heap.back() = h;
+        std::push_heap(heap.begin(), heap.end(), worse);
+      }
+    }
+  }
+  std::sort(heap.begin(), heap.end(), worse);
+  for (size_t k = 0; k < heap.size(); k++)
+  {
+    out_seqno[k] = heap[k].seqno;
+    out_score[k] = heap[k].score;
+  }
+  if (totalhits) *totalhits = tot;
+  if (obvious) *obvious = obv;
+  return (int64_t)heap.size();
+}
+
+int swb_set_mode(swb_db *db, int mode)
+{
+  if (!db || (mode != 0 && mode != 2)) return SWB_ERR_ARG;
+  db->mode = mode;
+  return SWB_OK;
+}
+
+int swb_db_open_ms(const swb_db *db, double *upload_ms, double *layout_ms)
+{
+  if (!db) return SWB_ERR_ARG;
+  if (upload_ms) *upload_ms = db->upload_ms;
+  if (layout_ms) *layout_ms = db->layout_ms;
+  return SWB_OK;
+}
+
+/* test hook: pin the scan kernel shape (G threads per stream, R rows per thread) and lane
+   arithmetic (0 = int16 DPX only, 1 = DPX + fp16-pattern adds); zeros / -1 restore the default. */
+int swb_set_shape(swb_db *db, int G, int R, int lane_mode)
+{
+  if (!db) return SWB_ERR_ARG;
+  if (G != 0)
+  {
+    bool found = false;
+    for (int i = 0; i < g_nshapes; i++) found = found || (g_shapes[i].G == G && g_shapes[i].R == R);
+    if (!found) return SWB_ERR_ARG;
+  }
+  if (lane_mode < -1 || lane_mode > 1) return SWB_ERR_ARG;
+  db->force_G = G; db->force_R = R; db->force_mode = lane_mode;
+  return SWB_OK;
+}
+
+}  // extern "C"

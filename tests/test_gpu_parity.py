@@ -1,0 +1,223 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Bar: bit-exact scores (integer work)."""
+import numpy as np
+import pytest
+
+import fixtures
+from swipe_b200 import Database, Scoring, scoring, synth
+
+pytestmark = pytest.mark.gpu
+
+B62 = scoring.blosum62()
+
+
+def _check(db, q, sc, oracle, residues, offsets, what=""):
+    got = db.search(q, sc)
+    exp, width, counts = oracle.scan(residues, offsets, q, sc.matrix, sc.gap_open, sc.gap_extend)
+    bad = np.nonzero(got != exp)[0]
+    assert bad.size == 0, "%s: %d/%d scores differ, first %s got %s exp %s len %s" % (
+        what, bad.size, exp.size, bad[:8], got[bad[:8]], exp[bad[:8]],
+        (offsets[1:] - offsets[:-1])[bad[:8]])
+    c = db.last_counters
+    assert [c["ref_width7"], c["ref_width16"], c["ref_width63"]] == \
+        [int((width == 7).sum()), int((width == 16).sum()), int((width == 63).sum())]
+    return got, c
+
+
+def test_known_answers(oracle):
+    """values obtained from the reference binary."""
+    q = scoring.encode_protein("HEAGAWGHEE")
+    subs = ["PAWHEAE", "HEAGAWGHEE", "W", "HEAGAWGHEEAAAAAAAAAAHEAGAWGHEE", "PPPPPPPP",
+            "HEAGAWWWWWWGHEE"]
+    residues, offsets = fixtures.pack([scoring.encode_protein(s) for s in subs])
+    with Database(residues, offsets) as db:
+        got = db.search(q, Scoring(B62, 11, 1))
+        assert got.tolist() == [17, 62, 11, 62, 0, 46]
+        db.set_mode(2)
+        assert db.search(q, Scoring(B62, 11, 1)).tolist() == [17, 62, 11, 62, 0, 46]
+
+
+@pytest.mark.parametrize("shape", [(0, 0, -1), (8, 8, 0), (8, 13, 1), (16, 24, 0), (16, 24, 1),
+                                   (32, 12, 0), (32, 12, 1), (32, 32, 1)])
+def test_edge_cases_all_shapes(oracle, shape):
+    q = synth.protein_query(375)
+    residues, offsets = fixtures.edge_db(q)
+    sc = Scoring(B62, 11, 1)
+    with Database(residues, offsets) as db:
+        db.set_shape(*shape)
+        _check(db, q, sc, oracle, residues, offsets, "edge %s" % (shape,))
+
+
+@pytest.mark.parametrize("qlen", [1, 2, 7, 100, 375, 1000, 1100])
+def test_query_lengths(oracle, qlen):
+    q = synth.protein_query(qlen, seed=100 + qlen)
+    residues, offsets = synth.protein_db(1500, query=q, seed=200 + qlen, plant_every=50,
+                                         max_len=1200)
+    with Database(residues, offsets) as db:
+        _check(db, q, Scoring(B62, 11, 1), oracle, residues, offsets, "qlen %d" % qlen)
+
+
+def test_multi_pass_small_shape(oracle):
+    """Forces 6 passes over a 375-row query with the smallest shape (64 rows per pass)."""
+    q = synth.protein_query(375)
+    residues, offsets = synth.protein_db(800, query=q, seed=11, plant_every=20, max_len=900)
+    with Database(residues, offsets) as db:
+        for lane_mode in (0, 1):
+            db.set_shape(8, 8, lane_mode)
+            _check(db, q, Scoring(B62, 11, 1), oracle, residues, offsets, "multipass")
+
+
+def test_requeue_limits(oracle):
+    """Self hits of growing length straddle the packed kernels' overflow limits (2047 - hi for
+    the fp16-pattern lanes, 32767 - hi for the int16 lanes) and the reference's own limits."""
+    rng = np.random.default_rng(5)
+    q = synth.protein_query(7000, seed=77)
+    subs = []
+    for L in (10, 20, 21, 22, 23, 24, 100, 350, 380, 385, 390, 395, 400, 1000, 6000, 6100, 6200, 6300, 7000):
+        subs.append(q[:L].copy())
+        subs.append(np.concatenate([synth.random_protein(rng, 13), q[5:L], synth.random_protein(rng, 3)]))
+    for _ in range(37):
+        subs.append(synth.random_protein(rng, int(rng.integers(20, 500))))
+    residues, offsets = fixtures.pack(subs)
+    sc = Scoring(B62, 11, 1)
+    with Database(residues, offsets) as db:
+        for lane_mode, limit in ((1, 2047 - 11), (0, 32767 - 11)):
+            db.set_shape(0, 0, lane_mode)
+            got, c = _check(db, q, sc, oracle, residues, offsets, "requeue mode %d" % lane_mode)
+            assert c["gpu_requeued"] == int((got >= limit).sum())
+            assert c["gpu_narrow"] + c["gpu_requeued"] == got.size
+        assert got.max() > 32767
+
+
+def test_wide_only_matches(oracle):
+    q = synth.protein_query(200, seed=9)
+    residues, offsets = fixtures.edge_db(q, seed=8)
+    with Database(residues, offsets) as db:
+        db.set_mode(2)
+        _check(db, q, Scoring(B62, 11, 1), oracle, residues, offsets, "wide")
+
+
+@pytest.mark.parametrize("gaps", [(11, 1), (10, 2), (0, 1), (5, 0), (0, 0), (40, 3)])
+def test_gap_penalties(oracle, gaps):
+    q = synth.protein_query(120, seed=31)
+    residues, offsets = synth.protein_db(600, query=q, seed=32, plant_every=10, max_len=600)
+    with Database(residues, offsets) as db:
+        _check(db, q, Scoring(B62, *gaps), oracle, residues, offsets, "gaps %s" % (gaps,))
+
+
+def test_asymmetric_matrix_and_all_symbols(oracle):
+    m = fixtures.asym_matrix()
+    rng = np.random.default_rng(12)
+    q = rng.integers(0, 28, size=333).astype(np.uint8)              # every code incl. '-' and '*'
+    subs = [rng.integers(0, 28, size=int(rng.integers(1, 300))).astype(np.uint8) for _ in range(301)]
+    subs.append(q.copy())
+    residues, offsets = fixtures.pack(subs)
+    with Database(residues, offsets) as db:
+        for lane_mode in (0, 1):
+            db.set_shape(0, 0, lane_mode)
+            _check(db, q, Scoring(m, 7, 2), oracle, residues, offsets, "asym")
+
+
+def test_many_query_symbols_fall_back_to_wide(oracle):
+    """More than 30 distinct query codes cannot use the packed table rows."""
+    q = np.arange(32, dtype=np.uint8)
+    rng = np.random.default_rng(2)
+    subs = [rng.integers(0, 32, size=int(rng.integers(1, 80))).astype(np.uint8) for _ in range(50)]
+    residues, offsets = fixtures.pack(subs)
+    with Database(residues, offsets) as db:
+        _check(db, q, Scoring(fixtures.asym_matrix(), 3, 1), oracle, residues, offsets, "32 symbols")
+
+
+def test_nucleotide_both_strands(oracle):
+    """Config 4 at parity size: +1/-3, gaps 5/2, both strands = two scans with the
+    reverse-complemented query (query.cc:337-342)."""
+    q = synth.dna_query(1000)
+    residues, offsets = synth.dna_db(3000, seed=4)
+    rng = np.random.default_rng(6)
+    # plant forward and reverse-complement copies of query windows, with an N run
+    lens = offsets[1:] - offsets[:-1]
+    for i in range(0, 3000, 100):
+        w = int(min(lens[i], 120))
+        s = int(rng.integers(0, 1000 - w))
+        piece = q[s:s + w].copy()
+        if i % 200 == 0:
+            piece = synth.revcomp_nt(piece)
+        if i % 300 == 0:
+            piece[10:14] = 15
+        residues[offsets[i]: offsets[i] + w] = piece
+    m = scoring.nucleotide_matrix(1, -3)
+    with Database(residues, offsets) as db:
+        for strand_q in (q, synth.revcomp_nt(q)):
+            _check(db, strand_q, Scoring(m, 5, 2), oracle, residues, offsets, "nt")
+
+
+def test_trailing_separator_layout(oracle):
+    """offsets into a raw .psq: NUL before the first and after every sequence (database.cc:1246)."""
+    q = synth.protein_query(90, seed=41)
+    subs_res, subs_off = synth.protein_db(300, query=q, seed=42, plant_every=10, max_len=300)
+    lens = subs_off[1:] - subs_off[:-1]
+    psq = [np.zeros(1, dtype=np.uint8)]
+    off = [1]
+    for i in range(300):
+        psq.append(subs_res[subs_off[i]:subs_off[i + 1]])
+        psq.append(np.zeros(1, dtype=np.uint8))
+        off.append(off[-1] + int(lens[i]) + 1)
+    psq = np.concatenate(psq)
+    off = np.array(off, dtype=np.int64)
+    with Database(psq, off, trailing=1) as db:
+        got = db.search(q, Scoring(B62, 11, 1))
+    exp, _, _ = oracle.scan(subs_res, subs_off, q, B62, 11, 1)
+    assert np.array_equal(got, exp)
+
+
+def test_search_list_and_end(oracle):
+    q = synth.protein_query(150, seed=51)
+    residues, offsets = synth.protein_db(400, query=q, seed=52, plant_every=7, max_len=500)
+    sc = Scoring(B62, 11, 1)
+    exp, _, _ = oracle.scan(residues, offsets, q, B62, 11, 1)
+    rng = np.random.default_rng(53)
+    with Database(residues, offsets) as db:
+        for n in (0, 1, 5, 77, 400):
+            sel = rng.permutation(400)[:n]
+            got = db.search_list(q, sc, sel)
+            assert np.array_equal(got, exp[sel]), "list of %d" % n
+        sel = np.argsort(-exp)[:40]
+        s, bp, bq = db.search_end(q, sc, sel)
+        assert np.array_equal(s, exp[sel])
+        for k, i in enumerate(sel):
+            es, ed, eq = oracle.score_end(residues[offsets[i]:offsets[i + 1]], q, B62, 11, 1)
+            assert (s[k], bp[k], bq[k]) == (es, ed, eq)
+
+
+def test_empty_inputs(oracle):
+    q = synth.protein_query(50, seed=61)
+    residues, offsets = fixtures.pack([np.zeros(0, dtype=np.uint8)] * 3)
+    sc = Scoring(B62, 11, 1)
+    with Database(residues, offsets) as db:
+        assert db.search(q, sc).tolist() == [0, 0, 0]
+    with Database(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)) as db:
+        assert db.search(q, sc).size == 0
+    residues, offsets = synth.protein_db(10, seed=62)
+    with Database(residues, offsets) as db:
+        assert db.search(np.zeros(0, dtype=np.uint8), sc).tolist() == [0] * 10
+
+
+def test_full_size_properties():
+    """BASELINE config-2-shaped run at a size the oracle cannot cover: size-independent checks.
+    (a) a second search returns identical scores; (b) scoring a list of the same subjects in a
+    different order gives the same per-subject scores (layout independence); (c) the wide kernel
+    agrees on a random sample; (d) planted self copies score the query's self score."""
+    q = synth.protein_query(375)
+    residues, offsets = synth.protein_db(200000, query=q, seed=71)
+    sc = Scoring(B62, 11, 1)
+    with Database(residues, offsets) as db:
+        a = db.search(q, sc)
+        b = db.search(q, sc)
+        assert np.array_equal(a, b)
+        rng = np.random.default_rng(72)
+        sel = rng.permutation(200000)[:30000]
+        assert np.array_equal(db.search_list(q, sc, sel), a[sel])
+        db.set_mode(2)
+        sel2 = sel[:3000]
+        assert np.array_equal(db.search_list(q, sc, sel2), a[sel2])
+        assert a.min() >= 0
