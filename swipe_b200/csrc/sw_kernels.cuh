@@ -30,7 +30,7 @@ typedef unsigned long long u64;
 #define SWB_PAD_CODE 32      // internal subject symbol for padding columns (scores SWB_PAD_SCORE)
 #define SWB_PAD_SCORE (-1)
 #define SWB_MROWS 33         // 32 symbol codes + the pad code
-#define SWB_SMEM_HEADER 2176  // the [33][32] s16 table, rounded up to 128 B
+#define SWB_SMEM_HEADER 2304  // the staged [33][34] s16 score matrix, rounded up to 128 B
 #define SWB_FLAG_START 1u
 #define SWB_FLAG_END 2u
 
@@ -43,11 +43,10 @@ struct ScanParams
   const int *stream_pair;     // [nstreams+1] first pair of every stream
   u32 *pair_scores;           // [npairs] packed lane maxima
   const short *m16;           // [33][32] score of (subject code, table row) in the mode's encoding
-  const unsigned short *qrow_off; // [npass*G*R] byte offset of every query row's table row
+  const unsigned short *qrow_off; // [npass*G*R] 16 * (table row of every query row)
   uint4 *bndH;                // [total_blocks] bottom H of a pass (only when npass > 1)
   uint4 *bndF;
   int nq;                     // table rows in use (distinct query symbols)
-  int slot_bytes;             // (nq + 2) * 16: rows, header row, pad row
   int npass;
   u32 negq;                   // both lanes: -(gap open + extend) in the mode's encoding
   u32 negr;                   // both lanes: -(gap extend), two's complement
@@ -91,44 +90,67 @@ __device__ __forceinline__ void swb_cell(u32 hd, u32 s, u32 &e, u32 &f, u32 &h, 
   }
 }
 
-template <int G, int R, int MODE>
-__global__ void __launch_bounds__(128) swb_scan_kernel(const ScanParams P)
+// Shared-memory geometry of the scan kernel (host and device agree through these).
+#define SWB_STREAMS 8                        // streams per CTA = threads per quarter-warp
+#define SWB_MS_STRIDE 34                     // halfwords per subject code in the staged score matrix
+#define SWB_XFER_WORDS 9                     // H[4], F[4], running maximum
+__host__ __device__ inline int swb_scan_threads(int G) { return SWB_STREAMS * G; }
+__host__ __device__ inline size_t swb_scan_smem(int G, int nq)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
-  unsigned short *Ms = (unsigned short *)smem;       // [33][32]
-  unsigned char *ring_base = smem + SWB_SMEM_HEADER;
+  const size_t warps = (size_t)(SWB_STREAMS * G) / 32;
+  return SWB_SMEM_HEADER + (size_t)(G + 1) * (nq + 2) * 128 + 2 * warps * SWB_XFER_WORDS * SWB_STREAMS * 4;
+}
 
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int g = lane % G;
-  const int grp = lane / G;
+// Thread geometry: a CTA runs 8 streams through G pipeline stages, thread = (stage g, stream k)
+// with k = tid & 7 and g = tid >> 3.  The 8 threads of a quarter-warp are therefore at the SAME
+// stage, i.e. on the same query rows, of 8 different streams; with the 8 streams' tables
+// interleaved (16 B per stream in every 128-B table row) their LDS.128 requests hit one
+// 128-B line: no bank conflicts, whatever the query symbols are.  Stage g hands its bottom row to
+// stage g+1 by a shuffle over 8 lanes inside a warp and through a double-buffered shared-memory
+// mailbox between warps; one __syncthreads per step orders tables, mailboxes and ring reuse
+// (the ring has G+1 slots so that the slot being rebuilt was last read before the barrier).
+template <int G, int R, int MODE>
+__global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const ScanParams P)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NSLOT = G + 1;
+  constexpr int NWARP = SWB_STREAMS * G / 32;
+  unsigned short *Ms = (unsigned short *)smem;       // [33][SWB_MS_STRIDE]
+  const int tid = threadIdx.x;
+  const int k = tid & 7;
+  const int g = tid >> 3;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
   const int nq = P.nq;
-  const int slot_bytes = P.slot_bytes;
+  const int slot_bytes = (nq + 2) * 128;
+  unsigned char *ring = smem + SWB_SMEM_HEADER;
+  u32 *xfer = (u32 *)(ring + (size_t)NSLOT * slot_bytes);    // [2][NWARP][9][8]
 
-  for (int i = threadIdx.x; i < SWB_MROWS * 32 / 2; i += blockDim.x)
-    ((u32 *)Ms)[i] = ((const u32 *)P.m16)[i];
-
-  unsigned char *ring = ring_base + (size_t)((warp * (32 / G) + grp) * G) * slot_bytes;
+  for (int i = tid; i < SWB_MROWS * 32; i += blockDim.x)
+    Ms[(i >> 5) * SWB_MS_STRIDE + (i & 31)] = ((const unsigned short *)P.m16)[i];
   // the pad row of every slot is written once; builds never touch it
-  *(uint4 *)(ring + g * slot_bytes + (nq + 1) * 16) =
-      make_uint4(P.padword, P.padword, P.padword, P.padword);
+  for (int i = tid; i < NSLOT * SWB_STREAMS; i += blockDim.x)
+    *(uint4 *)(ring + (i >> 3) * slot_bytes + (nq + 1) * 128 + (i & 7) * 16) =
+        make_uint4(P.padword, P.padword, P.padword, P.padword);
   __syncthreads();
 
-  const int stream = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 / G) + grp;
+  const int stream = blockIdx.x * SWB_STREAMS + k;
   const int p0 = P.stream_pair[stream];
   const int p1 = P.stream_pair[stream + 1];
   const long long b0 = P.pairblk[p0];
   const int nblk = (int)(P.pairblk[p1] - b0);
   const uint2 *blk = P.blocks + b0;
-  const int nsteps_warp = __reduce_max_sync(0xffffffffu, nblk);
-  const int nsteps = nsteps_warp > 0 ? nsteps_warp + G - 1 : 0;
+  const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);   // every warp holds all 8 streams
+  const int nsteps = nblk_max > 0 ? nblk_max + G - 1 : 0;
   const u32 negq = P.negq, negr = P.negr;
+  const bool first_quarter = (lane >> 3) == 0;
+  const bool last_quarter = (lane >> 3) == 3;
 
   for (int pass = 0; pass < P.npass; pass++)
   {
     u32 rq[R];
 #pragma unroll
-    for (int i = 0; i < R; i++) rq[i] = P.qrow_off[(pass * G + g) * R + i];
+    for (int i = 0; i < R; i++) rq[i] = (u32)P.qrow_off[(pass * G + g) * R + i] * 8u + (u32)k * 16u;
 
     u32 H[R], E[R];
 #pragma unroll
@@ -136,25 +158,28 @@ __global__ void __launch_bounds__(128) swb_scan_kernel(const ScanParams P)
     u32 smax = 0, dtop = 0;
     u32 ih0 = 0, ih1 = 0, ih2 = 0, ih3 = 0, if0 = 0, if1 = 0, if2 = 0, if3 = 0, is = 0;
     int pair_out = p0;
-    const bool feed = (pass > 0) && (g == 0);          // thread 0 reads the previous pass's bottom row
+    const bool feed = (pass > 0) && (g == 0);          // stage 0 reads the previous pass's bottom row
     const bool spill = (pass + 1 < P.npass) && (g == G - 1);
 
     uint2 cur = make_uint2(0, 0);
     if (nblk > 0) cur = blk[0];
+    int wslot = 0;                                     // t % NSLOT
+    int rslot = (NSLOT - (g % NSLOT)) % NSLOT;         // (t - g) mod NSLOT, kept non-negative
+    if (pass > 0) __syncthreads();                     // the previous pass is done with ring and mailboxes
 
     for (int t = 0; t < nsteps; t++)
     {
       uint2 nxt = make_uint2(0, 0);
       if (t + 1 < nblk) nxt = blk[t + 1];
 
-      // ---- build the score table of block t into slot t % G ---------------------------------
+      // ---- build the score tables of block t (8 streams) into slot t % NSLOT -----------------
       if (t < nblk)
       {
-        unsigned char *slot = ring + (t & (G - 1)) * slot_bytes;
-        const u32 a0 = (cur.x & 63u) * 32u, a1 = ((cur.x >> 8) & 63u) * 32u,
-                  a2 = ((cur.x >> 16) & 63u) * 32u, a3 = ((cur.x >> 24) & 63u) * 32u;
-        const u32 c0 = (cur.y & 63u) * 32u, c1 = ((cur.y >> 8) & 63u) * 32u,
-                  c2 = ((cur.y >> 16) & 63u) * 32u, c3 = ((cur.y >> 24) & 63u) * 32u;
+        unsigned char *slot = ring + wslot * slot_bytes + k * 16;
+        const u32 a0 = (cur.x & 63u) * SWB_MS_STRIDE, a1 = ((cur.x >> 8) & 63u) * SWB_MS_STRIDE,
+                  a2 = ((cur.x >> 16) & 63u) * SWB_MS_STRIDE, a3 = ((cur.x >> 24) & 63u) * SWB_MS_STRIDE;
+        const u32 c0 = (cur.y & 63u) * SWB_MS_STRIDE, c1 = ((cur.y >> 8) & 63u) * SWB_MS_STRIDE,
+                  c2 = ((cur.y >> 16) & 63u) * SWB_MS_STRIDE, c3 = ((cur.y >> 24) & 63u) * SWB_MS_STRIDE;
         for (int s = g; s < nq; s += G)
         {
           uint4 w;
@@ -162,19 +187,26 @@ __global__ void __launch_bounds__(128) swb_scan_kernel(const ScanParams P)
           w.y = __byte_perm(Ms[a1 + s], Ms[c1 + s], 0x5410);
           w.z = __byte_perm(Ms[a2 + s], Ms[c2 + s], 0x5410);
           w.w = __byte_perm(Ms[a3 + s], Ms[c3 + s], 0x5410);
-          *(uint4 *)(slot + s * 16) = w;
+          *(uint4 *)(slot + s * 128) = w;
         }
-        if (g == 0) *(u32 *)(slot + nq * 16) = (cur.x >> 6) & 3u;
+        if (g == 0) *(u32 *)(slot + nq * 128) = (cur.x >> 6) & 3u;
       }
-      __syncwarp();
+      __syncthreads();
 
-      // ---- thread g works on block t - g -------------------------------------------------------
+      // ---- stage g works on block t - g ------------------------------------------------------------
       const int b = t - g;
       u32 hup0 = 0, hup1 = 0, hup2 = 0, hup3 = 0, f0 = 0, f1 = 0, f2 = 0, f3 = 0;
       if (b >= 0 && b < nblk)
       {
-        const unsigned char *slot = ring + (b & (G - 1)) * slot_bytes;
-        const u32 flags = *(const u32 *)(slot + nq * 16);
+        const unsigned char *slot = ring + rslot * slot_bytes;
+        const u32 flags = *(const u32 *)(slot + nq * 128 + k * 16);
+        if (first_quarter && g > 0)
+        {
+          const u32 *x = xfer + (((t + 1) & 1) * NWARP + (warp - 1)) * (SWB_XFER_WORDS * 8) + k;
+          ih0 = x[0]; ih1 = x[8]; ih2 = x[16]; ih3 = x[24];
+          if0 = x[32]; if1 = x[40]; if2 = x[48]; if3 = x[56];
+          is = x[64];
+        }
         if (feed)
         {
           const uint4 vh = P.bndH[b0 + b], vf = P.bndF[b0 + b];
@@ -220,19 +252,27 @@ __global__ void __launch_bounds__(128) swb_scan_kernel(const ScanParams P)
         }
       }
 
-      // ---- hand the strip's bottom row to the next thread of the group ------------------------
-      ih0 = __shfl_up_sync(0xffffffffu, hup0, 1, G);
-      ih1 = __shfl_up_sync(0xffffffffu, hup1, 1, G);
-      ih2 = __shfl_up_sync(0xffffffffu, hup2, 1, G);
-      ih3 = __shfl_up_sync(0xffffffffu, hup3, 1, G);
-      if0 = __shfl_up_sync(0xffffffffu, f0, 1, G);
-      if1 = __shfl_up_sync(0xffffffffu, f1, 1, G);
-      if2 = __shfl_up_sync(0xffffffffu, f2, 1, G);
-      if3 = __shfl_up_sync(0xffffffffu, f3, 1, G);
-      is = __shfl_up_sync(0xffffffffu, smax, 1, G);
+      // ---- hand the strip's bottom row to the next stage --------------------------------------------
+      if (last_quarter && g < G - 1)
+      {
+        u32 *x = xfer + ((t & 1) * NWARP + warp) * (SWB_XFER_WORDS * 8) + k;
+        x[0] = hup0; x[8] = hup1; x[16] = hup2; x[24] = hup3;
+        x[32] = f0; x[40] = f1; x[48] = f2; x[56] = f3;
+        x[64] = smax;
+      }
+      ih0 = __shfl_up_sync(0xffffffffu, hup0, 8);
+      ih1 = __shfl_up_sync(0xffffffffu, hup1, 8);
+      ih2 = __shfl_up_sync(0xffffffffu, hup2, 8);
+      ih3 = __shfl_up_sync(0xffffffffu, hup3, 8);
+      if0 = __shfl_up_sync(0xffffffffu, f0, 8);
+      if1 = __shfl_up_sync(0xffffffffu, f1, 8);
+      if2 = __shfl_up_sync(0xffffffffu, f2, 8);
+      if3 = __shfl_up_sync(0xffffffffu, f3, 8);
+      is = __shfl_up_sync(0xffffffffu, smax, 8);
       if (g == 0) { ih0 = ih1 = ih2 = ih3 = 0; if0 = if1 = if2 = if3 = 0; is = 0; }
       cur = nxt;
-      __syncwarp();
+      wslot = wslot + 1 == NSLOT ? 0 : wslot + 1;
+      rslot = rslot + 1 == NSLOT ? 0 : rslot + 1;
     }
   }
 }

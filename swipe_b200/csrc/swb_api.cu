@@ -400,16 +400,18 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       SWB_TRY(build_layout(db, *L, d_list, n));
       launches += 5;
     }
-    // launch geometry: 4 warps per CTA, as many CTAs per SM as shared memory and registers allow
-    const int slot_bytes = (tb.nq + 2) * 16;
-    const size_t smem = SWB_SMEM_HEADER + (size_t)4 * 32 * slot_bytes;
+    // launch geometry: one CTA = 8 streams x G stages; as many CTAs per SM as shared memory
+    // and registers allow
+    const int threads = swb_scan_threads(shape->G);
+    const size_t smem = swb_scan_smem(shape->G, tb.nq);
     SWB_CUDA(cudaFuncSetAttribute((const void *)shape->fn,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)shape->fn, 128, smem));
+    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)shape->fn, threads,
+                                                           smem));
     if (occ < 1) return SWB_ERR_INTERNAL;
     const int grid = db->sm_count * occ;
-    const int nstreams = grid * 4 * (32 / shape->G);
+    const int nstreams = grid * SWB_STREAMS;
     if (L->stream_pair_n != nstreams)
     {
       SWB_TRY(L->stream_pair.reserve((size_t)nstreams + 1));
@@ -435,7 +437,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     P.blocks = L->blocks.p; P.pairblk = L->pairblk.p; P.stream_pair = L->stream_pair.p;
     P.pair_scores = L->pair_scores.p; P.m16 = db->m16.p; P.qrow_off = db->qrow_off.p;
     P.bndH = db->bndH.p; P.bndF = db->bndF.p;
-    P.nq = tb.nq; P.slot_bytes = slot_bytes; P.npass = npass;
+    P.nq = tb.nq; P.npass = npass;
     const long long q = sc->gap_open_extend, r = sc->gap_extend;
     const unsigned nq16 = (unsigned)(unsigned short)enc16(-q, mode);
     const unsigned nr16 = (unsigned)(unsigned short)(short)(-r);
@@ -443,7 +445,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
     const int limit = (mode == SWB_MODE_HYBRID ? 2047 : 32767) - (int)std::max<long long>(tb.hi, 0);
     SWB_CUDA(cudaEventRecord(db->ev[0], st));
-    shape->fn<<<grid, 128, smem, st>>>(P);
+    shape->fn<<<grid, threads, smem, st>>>(P);
     SWB_CUDA(cudaGetLastError());
     SWB_CUDA(cudaEventRecord(db->ev[1], st));
     launches++;
