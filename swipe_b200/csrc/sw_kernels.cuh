@@ -93,12 +93,12 @@ __device__ __forceinline__ void swb_cell(u32 hd, u32 s, u32 &e, u32 &f, u32 &h, 
 // Shared-memory geometry of the scan kernel (host and device agree through these).
 #define SWB_STREAMS 8                        // streams per CTA = threads per quarter-warp
 #define SWB_MS_STRIDE 34                     // halfwords per subject code in the staged score matrix
-#define SWB_XFER_WORDS 9                     // H[4], F[4], running maximum
+#define SWB_XFER_BYTES 48                    // mailbox entry per stream: H[4], F[4], running maximum (+pad)
 __host__ __device__ inline int swb_scan_threads(int G) { return SWB_STREAMS * G; }
 __host__ __device__ inline size_t swb_scan_smem(int G, int nq)
 {
   const size_t warps = (size_t)(SWB_STREAMS * G) / 32;
-  return SWB_SMEM_HEADER + (size_t)(G + 1) * (nq + 2) * 128 + 2 * warps * SWB_XFER_WORDS * SWB_STREAMS * 4;
+  return SWB_SMEM_HEADER + (size_t)(G + 1) * (nq + 2) * 128 + 2 * warps * SWB_STREAMS * SWB_XFER_BYTES;
 }
 
 // Thread geometry: a CTA runs 8 streams through G pipeline stages, thread = (stage g, stream k)
@@ -109,12 +109,22 @@ __host__ __device__ inline size_t swb_scan_smem(int G, int nq)
 // stage g+1 by a shuffle over 8 lanes inside a warp and through a double-buffered shared-memory
 // mailbox between warps; one __syncthreads per step orders tables, mailboxes and ring reuse
 // (the ring has G+1 slots so that the slot being rebuilt was last read before the barrier).
+//
+// Table build: after the barrier of step t the CTA builds the tables of block t+1 (read from
+// step t+1 on).  Thread (g, k) fills column g & 3 of rows g>>2, g>>2 + G/4, ... of stream k's
+// table: one residue pair to decode, two LDS.U16 + PRMT + STS.32 per word, and the 32 words a
+// warp stores at a time fill exactly one 128-B table row.
+//
+// The DP tile itself runs unconditionally (threads outside their stream's block range chew on
+// stale tables; only their side effects are predicated off), which keeps the whole step one
+// straight-line region for the instruction scheduler.
 template <int G, int R, int MODE>
 __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const ScanParams P)
 {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int NSLOT = G + 1;
   constexpr int NWARP = SWB_STREAMS * G / 32;
+  constexpr int RG = G / 4;                           // row groups of the table build
   unsigned short *Ms = (unsigned short *)smem;       // [33][SWB_MS_STRIDE]
   const int tid = threadIdx.x;
   const int k = tid & 7;
@@ -124,7 +134,7 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   const int nq = P.nq;
   const int slot_bytes = (nq + 2) * 128;
   unsigned char *ring = smem + SWB_SMEM_HEADER;
-  u32 *xfer = (u32 *)(ring + (size_t)NSLOT * slot_bytes);    // [2][NWARP][9][8]
+  unsigned char *xfer = ring + (size_t)NSLOT * slot_bytes;    // [2][NWARP][8] entries of 48 B
 
   for (int i = tid; i < SWB_MROWS * 32; i += blockDim.x)
     Ms[(i >> 5) * SWB_MS_STRIDE + (i & 31)] = ((const unsigned short *)P.m16)[i];
@@ -143,8 +153,22 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);   // every warp holds all 8 streams
   const int nsteps = nblk_max > 0 ? nblk_max + G - 1 : 0;
   const u32 negq = P.negq, negr = P.negr;
-  const bool first_quarter = (lane >> 3) == 0;
-  const bool last_quarter = (lane >> 3) == 3;
+  const bool first_quarter = (lane >> 3) == 0 && g > 0;
+  const bool last_quarter = (lane >> 3) == 3 && g < G - 1;
+  const int bcol = g & 3;                              // table column this thread builds
+  const int brow = g >> 2;                             // first table row it builds
+  const u32 bshift = 8u * (u32)bcol;
+  unsigned char *const bdst = ring + k * 16 + bcol * 4;
+
+  // builds column bcol of stream k's table for the block word pair (x, y) into slot `slot`
+  auto build = [&](const uint2 blkw, const int slot) {
+    const u32 da = ((blkw.x >> bshift) & 63u) * SWB_MS_STRIDE;
+    const u32 db = ((blkw.y >> bshift) & 63u) * SWB_MS_STRIDE;
+    unsigned char *dst = bdst + slot * slot_bytes;
+    for (int s = brow; s < nq; s += RG)
+      *(u32 *)(dst + s * 128) = __byte_perm(Ms[da + s], Ms[db + s], 0x5410);
+    if (g == 0) *(u32 *)(dst + nq * 128) = (blkw.x >> 6) & 3u;
+  };
 
   for (int pass = 0; pass < P.npass; pass++)
   {
@@ -161,104 +185,85 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
     const bool feed = (pass > 0) && (g == 0);          // stage 0 reads the previous pass's bottom row
     const bool spill = (pass + 1 < P.npass) && (g == G - 1);
 
-    uint2 cur = make_uint2(0, 0);
-    if (nblk > 0) cur = blk[0];
-    int wslot = 0;                                     // t % NSLOT
-    int rslot = (NSLOT - (g % NSLOT)) % NSLOT;         // (t - g) mod NSLOT, kept non-negative
     if (pass > 0) __syncthreads();                     // the previous pass is done with ring and mailboxes
+    uint2 nxt = make_uint2(0, 0);                      // block t + 1
+    if (nblk > 0) build(blk[0], 0);
+    if (nblk > 1) nxt = blk[1];
+    int wslot = 1;                                     // (t + 1) % NSLOT
+    int rslot = (NSLOT - g) % NSLOT;                   // (t - g) mod NSLOT, kept non-negative
 
     for (int t = 0; t < nsteps; t++)
     {
-      uint2 nxt = make_uint2(0, 0);
-      if (t + 1 < nblk) nxt = blk[t + 1];
-
-      // ---- build the score tables of block t (8 streams) into slot t % NSLOT -----------------
-      if (t < nblk)
-      {
-        unsigned char *slot = ring + wslot * slot_bytes + k * 16;
-        const u32 a0 = (cur.x & 63u) * SWB_MS_STRIDE, a1 = ((cur.x >> 8) & 63u) * SWB_MS_STRIDE,
-                  a2 = ((cur.x >> 16) & 63u) * SWB_MS_STRIDE, a3 = ((cur.x >> 24) & 63u) * SWB_MS_STRIDE;
-        const u32 c0 = (cur.y & 63u) * SWB_MS_STRIDE, c1 = ((cur.y >> 8) & 63u) * SWB_MS_STRIDE,
-                  c2 = ((cur.y >> 16) & 63u) * SWB_MS_STRIDE, c3 = ((cur.y >> 24) & 63u) * SWB_MS_STRIDE;
-        for (int s = g; s < nq; s += G)
-        {
-          uint4 w;
-          w.x = __byte_perm(Ms[a0 + s], Ms[c0 + s], 0x5410);
-          w.y = __byte_perm(Ms[a1 + s], Ms[c1 + s], 0x5410);
-          w.z = __byte_perm(Ms[a2 + s], Ms[c2 + s], 0x5410);
-          w.w = __byte_perm(Ms[a3 + s], Ms[c3 + s], 0x5410);
-          *(uint4 *)(slot + s * 128) = w;
-        }
-        if (g == 0) *(u32 *)(slot + nq * 128) = (cur.x >> 6) & 3u;
-      }
       __syncthreads();
+      // ---- tables of block t + 1 (first read after the next barrier) ------------------------------
+      const uint2 cur = nxt;
+      if (t + 2 < nblk) nxt = blk[t + 2];
+      if (t + 1 < nblk) build(cur, wslot);
 
       // ---- stage g works on block t - g ------------------------------------------------------------
       const int b = t - g;
-      u32 hup0 = 0, hup1 = 0, hup2 = 0, hup3 = 0, f0 = 0, f1 = 0, f2 = 0, f3 = 0;
-      if (b >= 0 && b < nblk)
+      const bool active = b >= 0 && b < nblk;
+      const unsigned char *slot = ring + rslot * slot_bytes;
+      const u32 flags = *(const u32 *)(slot + nq * 128 + k * 16);
+      if (first_quarter)
       {
-        const unsigned char *slot = ring + rslot * slot_bytes;
-        const u32 flags = *(const u32 *)(slot + nq * 128 + k * 16);
-        if (first_quarter && g > 0)
-        {
-          const u32 *x = xfer + (((t + 1) & 1) * NWARP + (warp - 1)) * (SWB_XFER_WORDS * 8) + k;
-          ih0 = x[0]; ih1 = x[8]; ih2 = x[16]; ih3 = x[24];
-          if0 = x[32]; if1 = x[40]; if2 = x[48]; if3 = x[56];
-          is = x[64];
-        }
-        if (feed)
-        {
-          const uint4 vh = P.bndH[b0 + b], vf = P.bndF[b0 + b];
-          ih0 = vh.x; ih1 = vh.y; ih2 = vh.z; ih3 = vh.w;
-          if0 = vf.x; if1 = vf.y; if2 = vf.z; if3 = vf.w;
-        }
-        if (flags & SWB_FLAG_START)
-        {
+        const unsigned char *x = xfer + ((((t + 1) & 1) * NWARP + (warp - 1)) * 8 + k) * SWB_XFER_BYTES;
+        const uint4 vh = *(const uint4 *)x, vf = *(const uint4 *)(x + 16);
+        ih0 = vh.x; ih1 = vh.y; ih2 = vh.z; ih3 = vh.w;
+        if0 = vf.x; if1 = vf.y; if2 = vf.z; if3 = vf.w;
+        is = *(const u32 *)(x + 32);
+      }
+      if (feed && active)
+      {
+        const uint4 vh = P.bndH[b0 + b], vf = P.bndF[b0 + b];
+        ih0 = vh.x; ih1 = vh.y; ih2 = vh.z; ih3 = vh.w;
+        if0 = vf.x; if1 = vf.y; if2 = vf.z; if3 = vf.w;
+      }
+      if (flags & SWB_FLAG_START)
+      {
 #pragma unroll
-          for (int i = 0; i < R; i++) { H[i] = 0; E[i] = 0; }
-          smax = 0;
-          dtop = 0;
-        }
-        smax = __vmaxs2(smax, is);
-        hup0 = ih0; hup1 = ih1; hup2 = ih2; hup3 = ih3;
-        f0 = if0; f1 = if1; f2 = if2; f3 = if3;
-        u32 dg = dtop;
+        for (int i = 0; i < R; i++) { H[i] = 0; E[i] = 0; }
+        smax = 0;
+        dtop = 0;
+      }
+      smax = __vmaxs2(smax, is);
+      u32 hup0 = ih0, hup1 = ih1, hup2 = ih2, hup3 = ih3;
+      u32 f0 = if0, f1 = if1, f2 = if2, f3 = if3;
+      u32 dg = dtop;
 #pragma unroll
-        for (int i = 0; i < R; i++)
-        {
-          const uint4 sc = *(const uint4 *)(slot + rq[i]);
-          u32 hd = dg, e = E[i], h;
-          dg = H[i];
-          swb_cell<MODE>(hd, sc.x, e, f0, h, smax, negq, negr); hd = hup0; hup0 = h;
-          swb_cell<MODE>(hd, sc.y, e, f1, h, smax, negq, negr); hd = hup1; hup1 = h;
-          swb_cell<MODE>(hd, sc.z, e, f2, h, smax, negq, negr); hd = hup2; hup2 = h;
-          swb_cell<MODE>(hd, sc.w, e, f3, h, smax, negq, negr); hup3 = h;
-          H[i] = h;
-          E[i] = e;
-        }
-        dtop = ih3;
-        if (spill)
-        {
-          P.bndH[b0 + b] = make_uint4(hup0, hup1, hup2, hup3);
-          P.bndF[b0 + b] = make_uint4(f0, f1, f2, f3);
-        }
-        if (g == G - 1 && (flags & SWB_FLAG_END))
-        {
-          u32 v = smax;
-          if (pass > 0) v = __vmaxs2(v, P.pair_scores[pair_out]);
-          P.pair_scores[pair_out] = v;
-          pair_out++;
-        }
+      for (int i = 0; i < R; i++)
+      {
+        const uint4 sc = *(const uint4 *)(slot + rq[i]);
+        u32 hd = dg, e = E[i], h;
+        dg = H[i];
+        swb_cell<MODE>(hd, sc.x, e, f0, h, smax, negq, negr); hd = hup0; hup0 = h;
+        swb_cell<MODE>(hd, sc.y, e, f1, h, smax, negq, negr); hd = hup1; hup1 = h;
+        swb_cell<MODE>(hd, sc.z, e, f2, h, smax, negq, negr); hd = hup2; hup2 = h;
+        swb_cell<MODE>(hd, sc.w, e, f3, h, smax, negq, negr); hup3 = h;
+        H[i] = h;
+        E[i] = e;
+      }
+      dtop = ih3;
+      if (spill && active)
+      {
+        P.bndH[b0 + b] = make_uint4(hup0, hup1, hup2, hup3);
+        P.bndF[b0 + b] = make_uint4(f0, f1, f2, f3);
+      }
+      if (g == G - 1 && active && (flags & SWB_FLAG_END))
+      {
+        u32 v = smax;
+        if (pass > 0) v = __vmaxs2(v, P.pair_scores[pair_out]);
+        P.pair_scores[pair_out] = v;
+        pair_out++;
       }
 
       // ---- hand the strip's bottom row to the next stage --------------------------------------------
-      if (last_quarter && g < G - 1)
+      if (last_quarter)
       {
-        u32 *x = xfer + ((t & 1) * NWARP + warp) * (SWB_XFER_WORDS * 8) + k;
-        x[0] = hup0; x[8] = hup1; x[16] = hup2; x[24] = hup3;
-        x[32] = f0; x[40] = f1; x[48] = f2; x[56] = f3;
-        x[64] = smax;
+        unsigned char *x = xfer + (((t & 1) * NWARP + warp) * 8 + k) * SWB_XFER_BYTES;
+        *(uint4 *)x = make_uint4(hup0, hup1, hup2, hup3);
+        *(uint4 *)(x + 16) = make_uint4(f0, f1, f2, f3);
+        *(u32 *)(x + 32) = smax;
       }
       ih0 = __shfl_up_sync(0xffffffffu, hup0, 8);
       ih1 = __shfl_up_sync(0xffffffffu, hup1, 8);
@@ -270,7 +275,6 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       if3 = __shfl_up_sync(0xffffffffu, f3, 8);
       is = __shfl_up_sync(0xffffffffu, smax, 8);
       if (g == 0) { ih0 = ih1 = ih2 = ih3 = 0; if0 = if1 = if2 = if3 = 0; is = 0; }
-      cur = nxt;
       wslot = wslot + 1 == NSLOT ? 0 : wslot + 1;
       rslot = rslot + 1 == NSLOT ? 0 : rslot + 1;
     }
