@@ -248,7 +248,9 @@ void ref_search16s(const unsigned char *residues, const int64_t *offsets, long n
   BYTE *dprofile = (BYTE *)xmalloc(4 * 16 * 32);
   BYTE *hearray = (BYTE *)xmalloc((qlen > 0 ? qlen : 1) * 32);
   BYTE **qtable = (BYTE **)xmalloc(sizeof(BYTE *) * (qlen > 0 ? qlen : 1));
-  for (long i = 0; i < qlen; i++) qtable[i] = dprofile + 64 * q[i];
+  // the alignment phase builds 8 channels x 1 column profiles: 16 bytes per query symbol
+  // (swipe.cc:225-255), not the 64 of the search phase (swipe.cc:1202-1232)
+  for (long i = 0; i < qlen; i++) qtable[i] = dprofile + 16 * q[i];
   std::vector<long> in(nseq), sc(nseq), bp(nseq), bq(nseq);
   for (long i = 0; i < nseq; i++) in[i] = i << 3;
   db_thread_s *dbta[8];                       // one handle per SIMD channel (swipe.cc:386)
