@@ -66,6 +66,8 @@ template <int MODE>
 __device__ __forceinline__ void swb_cell(u32 hd, u32 s, u32 &e, u32 &f, u32 &h, u32 &smax,
                                          const u32 negq, const u32 negr)
 {
+  const u32 r16_ = (0u - (negr & 0xffffu)) & 0x7fffu;
+  const u32 P_NEGR_FP = r16_ ? ((r16_ | (r16_ << 16)) | 0x80008000u) : 0u;  // -r as fp16 patterns
   if (MODE == SWB_MODE_INT16)
   {
     u32 t = __viaddmax_s16x2(hd, s, e);        // max(hd + s, e)
@@ -74,6 +76,28 @@ __device__ __forceinline__ void swb_cell(u32 hd, u32 s, u32 &e, u32 &f, u32 &h, 
     u32 hq = __vadd2(h, negq);                 // h - (open + extend)
     e = __viaddmax_s16x2(e, negr, hq);         // max(e - extend, h - open - extend)
     f = __viaddmax_s16x2(f, negr, hq);
+  }
+  else if (MODE == 2)
+  {
+    // experiment: 2-source max ops only (no VIMNMX3)
+    u32 a = swb_hadd2(hd, s);
+    u32 m = __vmaxs2(e, f);
+    h = __vimax_s16x2_relu(a, m);
+    smax = __vmaxs2(smax, h);
+    u32 hq = swb_hadd2(h, negq);
+    e = __viaddmax_s16x2_relu(e, negr, hq);
+    f = __viaddmax_s16x2_relu(f, negr, hq);
+  }
+  else if (MODE == 3)
+  {
+    // experiment: F through the FMA pipe (fp16-pattern add) + 2-source max
+    u32 a = swb_hadd2(hd, s);
+    h = __vimax3_s16x2_relu(a, e, f);
+    smax = __vmaxs2(smax, h);
+    u32 hq = swb_hadd2(h, negq);
+    e = __viaddmax_s16x2_relu(e, negr, hq);
+    u32 fr = swb_hadd2(f, P_NEGR_FP);
+    f = __vmaxs2(fr, hq);
   }
   else
   {

@@ -190,7 +190,7 @@ struct Tables
 
 inline short enc16(long long v, int mode)
 {
-  if (mode == SWB_MODE_HYBRID && v < 0) return (short)(0x8000u | (unsigned)(-v));
+  if (mode != SWB_MODE_INT16 && v < 0) return (short)(0x8000u | (unsigned)(-v));
   return (short)v;
 }
 
@@ -239,10 +239,14 @@ struct ShapeEntry { int G, R, mode; scan_fn fn; };
 #define SWB_SHAPE(G, R)                                           \
   {G, R, SWB_MODE_INT16, swb_scan_kernel<G, R, SWB_MODE_INT16>},  \
   {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID>}
+#define SWB_SHAPE_X(G, R)                                         \
+  {G, R, SWB_MODE_INT16, swb_scan_kernel<G, R, SWB_MODE_INT16>},  \
+  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID>},\
+  {G, R, 2, swb_scan_kernel<G, R, 2>}, {G, R, 3, swb_scan_kernel<G, R, 3>}
 
 const ShapeEntry g_shapes[] = {
     SWB_SHAPE(8, 8),   SWB_SHAPE(8, 13),  SWB_SHAPE(8, 16),  SWB_SHAPE(16, 12), SWB_SHAPE(16, 16),
-    SWB_SHAPE(16, 20), SWB_SHAPE(16, 24), SWB_SHAPE(32, 12), SWB_SHAPE(32, 16), SWB_SHAPE(32, 20),
+    SWB_SHAPE(16, 20), SWB_SHAPE_X(16, 24), SWB_SHAPE(32, 12), SWB_SHAPE(32, 16), SWB_SHAPE(32, 20),
     SWB_SHAPE(32, 24), SWB_SHAPE(32, 28), SWB_SHAPE(32, 32),
 };
 const int g_nshapes = (int)(sizeof(g_shapes) / sizeof(g_shapes[0]));
@@ -349,7 +353,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
   {
     Tables probe;
     SWB_TRY(prepare_tables(probe, query, qlen, sc, mode, 0));
-    if (mode == SWB_MODE_HYBRID && !probe.hybrid_ok) mode = SWB_MODE_INT16;
+    if (mode != SWB_MODE_INT16 && !probe.hybrid_ok) mode = SWB_MODE_INT16;
   }
   const ShapeEntry *shape = choose_shape(db, qlen, mode, &npass);
   if (!shape) return SWB_ERR_INTERNAL;
@@ -443,7 +447,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     const unsigned nr16 = (unsigned)(unsigned short)(short)(-r);
     const unsigned pad16 = (unsigned)(unsigned short)enc16(SWB_PAD_SCORE, mode);
     P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
-    const int limit = (mode == SWB_MODE_HYBRID ? 2047 : 32767) - (int)std::max<long long>(tb.hi, 0);
+    const int limit = (mode != SWB_MODE_INT16 ? 2047 : 32767) - (int)std::max<long long>(tb.hi, 0);
     SWB_CUDA(cudaEventRecord(db->ev[0], st));
     shape->fn<<<grid, threads, smem, st>>>(P);
     SWB_CUDA(cudaGetLastError());
@@ -788,7 +792,7 @@ int swb_set_shape(swb_db *db, int G, int R, int lane_mode)
     for (int i = 0; i < g_nshapes; i++) found = found || (g_shapes[i].G == G && g_shapes[i].R == R);
     if (!found) return SWB_ERR_ARG;
   }
-  if (lane_mode < -1 || lane_mode > 1) return SWB_ERR_ARG;
+  if (lane_mode < -1 || lane_mode > 3) return SWB_ERR_ARG;
   db->force_G = G; db->force_R = R; db->force_mode = lane_mode;
   return SWB_OK;
 }

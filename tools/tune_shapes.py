@@ -8,6 +8,9 @@ nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 2000000
 qlens = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [375]
 shapes = [(8, 8), (8, 13), (8, 16), (16, 12), (16, 16), (16, 20), (16, 24), (32, 12), (32, 16),
           (32, 20), (32, 24), (32, 28), (32, 32)]
+if len(sys.argv) > 3:
+    shapes = [tuple(int(v) for v in x.split("x")) for x in sys.argv[3].split(",")]
+modes = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 0]
 q0 = synth.protein_query(375)
 residues, offsets = synth.protein_db(nseq, query=q0)
 sc = Scoring(scoring.blosum62(), 11, 1)
@@ -17,7 +20,7 @@ with Database(residues, offsets) as db:
         q = synth.protein_query(qlen)
         cells = float(offsets[-1]) * qlen
         ref = None
-        for lane_mode in (1, 0):
+        for lane_mode in modes:
             for (G, R) in shapes:
                 npass = -(-qlen // (G * R))
                 if npass > 3 and qlen > 200:
