@@ -37,7 +37,7 @@ TOPK = 100                                  # the reference keeps max(-v, -b) = 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nseq", type=int, default=NSEQ, help="subjects per GPU shard")
@@ -240,20 +240,29 @@ def main():
     h2d = total_res + 8 * (nseq + 1) + args.qlen + 8 * 1024 + 33 * 32 * 2 + 2 * 1024
     d2h = 8 * nseq + 64
     if not args.no_e2e:
+        split = np.zeros(4)
+
         def e2e_step():
+            t0 = time.perf_counter()
             d = Database(pin_res.u8, pin_off.view(np.int64), device=local_rank,
-                         stream=stream.cuda_stream)
+                         stream=stream.cuda_stream, wait=False)   # upload / re-layout / scan overlap
             if shape:
                 d.set_shape(*shape)
+            t1 = time.perf_counter()
             d.search(q, sc, out=scores)
+            t2 = time.perf_counter()
             k = d.last_counters["kernel_launches"]
             d.close()
+            t3 = time.perf_counter()
             topk_merge([scores], [rank * nseq], TOPK, min_score=1)
+            t4 = time.perf_counter()
+            split[:] += (t1 - t0, t2 - t1, t3 - t2, t4 - t3)
             return k
         for _ in range(max(1, min(args.warmup, 2))):
             e2e_step()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        split[:] = 0
         f0.record(stream)
         for _ in range(args.steps):
             e2e_step()
@@ -325,7 +334,9 @@ def main():
         if e2e_all:
             line["e2e"] = {"value": cells_all * args.steps / (e2e_all * 1e-3) * 1e-9, "unit": "GCUPS",
                            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                           "ms_per_step": e2e_all / args.steps}
+                           "ms_per_step": e2e_all / args.steps,
+                           "host_ms": dict(zip(["open_enqueue", "search", "close", "topk"],
+                                               [round(float(x) * 1e3 / args.steps, 2) for x in split]))}
         if world == 1 and not args.no_cpu_baseline:
             g, kind, desc = run_reference_cpu(q, residues, offsets, 12.0, cores)
             line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": kind,

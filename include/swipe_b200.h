@@ -91,6 +91,9 @@ int swb_device_count(int *count);                    /* SWB_ERR_NO_DEVICE when t
 /* Pinned host memory for callers that want full-speed uploads (optional). */
 int swb_host_alloc(void **ptr, int64_t bytes);
 int swb_host_free(void *ptr);
+/* Device buffers of closed handles are kept for reuse (cudaMalloc/cudaFree synchronise the device);
+ * swb_trim() returns them to the driver. */
+int swb_trim(void);
 
 /* ---- database shard ----------------------------------------------------------------------
  * Replaces db_mapsequences + the db_getsequence pulls the reference kernels make while they
@@ -109,6 +112,13 @@ int swb_host_free(void *ptr);
  */
 int swb_db_open(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
                 int trailing, void *stream, swb_db **db);
+/* Same, but returns as soon as the copies and re-layout kernels are enqueued: the shard is cut
+ * into ~256 MB chunks whose upload, re-layout and (once swb_search is called) scan overlap.  The
+ * host buffers must stay valid and unchanged until swb_db_wait() or the first search on the
+ * handle has returned.                                                                         */
+int swb_db_open_async(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
+                      int trailing, void *stream, swb_db **db);
+int swb_db_wait(swb_db *db);
 int swb_db_close(swb_db *db);
 int swb_db_info(const swb_db *db, int64_t *nseq, int64_t *total_residues, int64_t *longest);
 
@@ -154,7 +164,8 @@ int64_t swb_topk_merge(int nshards, const int64_t *const *scores, const int64_t 
 /* Forces every subject through one kernel family: 0 = cascade (default), 1 = packed 16-bit
  * lanes only is not allowed (would not be exact) -> rejected; 2 = wide kernel for everything.  */
 int swb_set_mode(swb_db *db, int mode);
-/* Device time of the last swb_db_open's upload + re-layout, in ms. */
+/* Device time of the open: first byte sent .. last chunk laid out, and first layout kernel ..
+ * last chunk laid out (the two overlap), in ms.  Waits for the open to finish.                 */
 int swb_db_open_ms(const swb_db *db, double *upload_ms, double *layout_ms);
 /* Test hook: pin the scan kernel shape (G threads per stream, R query rows per thread) and the
  * lane arithmetic (0 = DPX int16 only, 1 = DPX + fp16-pattern adds); (0, 0, -1) = automatic.   */

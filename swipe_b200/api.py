@@ -15,7 +15,7 @@ STATUS = {0: "SWB_OK", -1: "SWB_ERR_ARG", -2: "SWB_ERR_NO_DEVICE", -3: "SWB_ERR_
 EXPORTS = ["swb_abi_version", "swb_strerror", "swb_last_cuda_error", "swb_device_count",
            "swb_host_alloc", "swb_host_free", "swb_db_open", "swb_db_close", "swb_db_info",
            "swb_search", "swb_search_list", "swb_search_end", "swb_topk_merge", "swb_set_mode",
-           "swb_db_open_ms", "swb_set_shape"]
+           "swb_db_open_ms", "swb_set_shape", "swb_db_open_async", "swb_db_wait", "swb_trim"]
 
 
 class SwbError(RuntimeError):
@@ -63,6 +63,9 @@ def load_library():
     lib.swb_host_free.argtypes = [C.c_void_p]
     lib.swb_db_open.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                 C.POINTER(C.c_void_p)]
+    lib.swb_db_open_async.argtypes = lib.swb_db_open.argtypes
+    lib.swb_db_wait.argtypes = [C.c_void_p]
+    lib.swb_trim.restype = C.c_int
     lib.swb_db_close.argtypes = [C.c_void_p]
     lib.swb_db_info.argtypes = [C.c_void_p, p64, p64, p64]
     lib.swb_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Scoring), C.c_void_p,
@@ -79,7 +82,7 @@ def load_library():
     lib.swb_set_shape.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     for name in ("swb_device_count", "swb_host_alloc", "swb_host_free", "swb_db_open",
                  "swb_db_close", "swb_db_info", "swb_search", "swb_search_list", "swb_search_end",
-                 "swb_set_mode", "swb_db_open_ms", "swb_set_shape"):
+                 "swb_set_mode", "swb_db_open_ms", "swb_set_shape", "swb_db_open_async", "swb_db_wait"):
         getattr(lib, name).restype = C.c_int
     _LIB = lib
     return lib
@@ -155,16 +158,16 @@ def _u8(a):
 class Database:
     """One database shard resident on one GPU (swb_db)."""
 
-    def __init__(self, residues, offsets, device=0, trailing=0, stream=None):
+    def __init__(self, residues, offsets, device=0, trailing=0, stream=None, wait=True):
         lib = load_library()
         self._lib = lib
         self._residues = _u8(residues)
         self._offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         self.nseq = int(self._offsets.size - 1)
         self._h = C.c_void_p()
-        _check(lib.swb_db_open(int(device), self._residues.ctypes.data, self._offsets.ctypes.data,
-                               self.nseq, int(trailing), C.c_void_p(stream or 0),
-                               C.byref(self._h)))
+        opener = lib.swb_db_open if wait else lib.swb_db_open_async
+        _check(opener(int(device), self._residues.ctypes.data, self._offsets.ctypes.data,
+                      self.nseq, int(trailing), C.c_void_p(stream or 0), C.byref(self._h)))
         self.last_counters = None
 
     def close(self):
@@ -183,6 +186,9 @@ class Database:
             self.close()
         except Exception:
             pass
+
+    def wait(self):
+        _check(self._lib.swb_db_wait(self._h))
 
     def info(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

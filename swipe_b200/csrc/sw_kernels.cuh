@@ -465,18 +465,18 @@ __global__ void swb_partition_kernel(const long long *pairblk, long long npairs,
 // unpack lane maxima into per-subject scores; lanes at or above the limit are queued for the
 // wide kernel instead (the reference's re-queue, swipe.cc:1459-1479, :1514-1537)
 __global__ void swb_finish_kernel(const u32 *pair_scores, const u32 *sorted_idx, long long n,
-                                  int limit, long long *scores, long long *requeue,
-                                  unsigned long long *nrequeue)
+                                  long long first, int limit, long long *scores,
+                                  long long *requeue, unsigned long long *nrequeue)
 {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const u32 w = pair_scores[k >> 1];
   const int v = (int)((k & 1) ? (w >> 16) : (w & 0xffffu));
-  const u32 pos = sorted_idx[k];                 // position in the caller's list
+  const long long pos = first + sorted_idx[k];   // position in the caller's list / shard
   if (v >= limit)
   {
     const unsigned long long slot = atomicAdd(nrequeue, 1ull);
-    requeue[slot] = (long long)pos;
+    requeue[slot] = pos;
   }
   else
     scores[pos] = v;

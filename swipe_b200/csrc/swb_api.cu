@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -47,26 +49,92 @@ thread_local std::string g_cuda_error;
     if (rc_ != SWB_OK) return rc_;    \
   } while (0)
 
+// Device allocations are recycled through a small per-process cache: opening and closing a shard
+// per search (the end-to-end path) would otherwise spend more time in cudaMalloc / cudaFree --
+// which also synchronise the device -- than in the scan.  Sizes are rounded up to 1/8 octave.
+struct DevCache
+{
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void *> free_blocks;
+  size_t cached = 0;
+  static size_t round_up(size_t bytes)
+  {
+    size_t b = bytes < 512 ? 512 : bytes;
+    size_t p = 512;
+    while (p < b) p <<= 1;
+    const size_t step = p >> 4 ? p >> 4 : 1;        // p/2 < b <= p: granularity p/16
+    return (b + step - 1) / step * step;
+  }
+  void *take(int dev, size_t rounded)
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = free_blocks.find(std::make_pair(dev, rounded));
+    if (it == free_blocks.end()) return nullptr;
+    void *p = it->second;
+    free_blocks.erase(it);
+    cached -= rounded;
+    return p;
+  }
+  void give(int dev, size_t rounded, void *p)
+  {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (cached + rounded <= (size_t)48 << 30)
+      {
+        free_blocks.emplace(std::make_pair(dev, rounded), p);
+        cached += rounded;
+        return;
+      }
+    }
+    cudaFree(p);
+  }
+  void trim()
+  {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto &kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached = 0;
+  }
+};
+DevCache g_cache;
+
 template <typename T> struct DevBuf
 {
   T *p = nullptr;
-  size_t cap = 0;
+  size_t cap = 0;        // elements
+  size_t bytes = 0;      // rounded allocation size
+  int dev = 0;
   int reserve(size_t n)
   {
     if (n <= cap && p) return SWB_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = n ? n : 1;
-    SWB_CUDA(cudaMalloc((void **)&p, want * sizeof(T)));
-    cap = want;
+    release();
+    const size_t want = DevCache::round_up((n ? n : 1) * sizeof(T));
+    int d = 0;
+    SWB_CUDA(cudaGetDevice(&d));
+    void *q = g_cache.take(d, want);
+    if (!q)
+    {
+      cudaError_t e = cudaMalloc(&q, want);
+      if (e == cudaErrorMemoryAllocation)
+      {
+        (void)cudaGetLastError();
+        g_cache.trim();                         // give cached blocks back and retry once
+        e = cudaMalloc(&q, want);
+      }
+      SWB_CUDA(e);
+    }
+    p = (T *)q;
+    bytes = want;
+    cap = want / sizeof(T);
+    dev = d;
     return SWB_OK;
   }
   void release()
   {
-    if (p) cudaFree(p);
+    if (p) g_cache.give(dev, bytes, p);
     p = nullptr;
     cap = 0;
+    bytes = 0;
   }
 };
 
@@ -74,9 +142,12 @@ template <typename T> struct DevBuf
 // into 4-column blocks.  Built for the whole shard at open time and for ad-hoc lists.
 struct Layout
 {
+  long long first = 0;    // first subject of the chunk (0 for list layouts)
   long long n = 0;        // subjects
   long long npairs = 0;
   long long cap_blocks = 0;
+  long long res_bytes = 0;                          // bound of the residues it covers
+  cudaEvent_t ev_ready = nullptr;                   // layout complete (recorded on the layout stream)
   DevBuf<u32> keys_in, keys_out, idx_in, idx_out;   // idx_out[k] = list position of k-th longest
   DevBuf<long long> nblk, pairblk;                  // [npairs+1]
   DevBuf<uint2> blocks;
@@ -89,6 +160,8 @@ struct Layout
     keys_in.release(); keys_out.release(); idx_in.release(); idx_out.release();
     nblk.release(); pairblk.release(); blocks.release(); cub_tmp.release();
     pair_scores.release(); stream_pair.release();
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    ev_ready = nullptr;
   }
 };
 
@@ -107,8 +180,12 @@ struct swb_db
   int mode = 0;
   DevBuf<unsigned char> residues;
   DevBuf<long long> offsets;
-  Layout all;      // the whole shard
+  std::vector<Layout *> chunks;   // the whole shard, cut into upload/layout/scan pipeline chunks
   Layout tmp;      // ad-hoc list layouts
+  cudaStream_t copy_stream = nullptr, layout_stream = nullptr;
+  cudaEvent_t ev_uploaded = nullptr;   // every byte of the shard is on the device
+  cudaEvent_t ev_open[3] = {nullptr, nullptr, nullptr};
+  bool opened_sync = false;
   // per-search device scratch
   DevBuf<short> m16;
   DevBuf<unsigned short> qrow_off;
@@ -126,9 +203,10 @@ struct swb_db
 namespace
 {
 
-int build_layout(swb_db *db, Layout &L, const long long *d_list, long long n)
+int build_layout(swb_db *db, Layout &L, const long long *d_list, long long first, long long n,
+                 long long res_bound, cudaStream_t st)
 {
-  cudaStream_t st = db->stream;
+  L.first = first;
   L.n = n;
   L.npairs = (n + 1) / 2;
   L.stream_pair_n = -1;
@@ -139,7 +217,8 @@ int build_layout(swb_db *db, Layout &L, const long long *d_list, long long n)
   SWB_TRY(L.nblk.reserve(L.npairs + 1)); SWB_TRY(L.pairblk.reserve(L.npairs + 1));
   SWB_TRY(L.pair_scores.reserve(L.npairs));
   const int T = 256;
-  swb_len_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(db->offsets.p, db->trailing, d_list, n,
+  const long long *offs = db->offsets.p + first;       // subject k of the chunk = first + k
+  swb_len_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(offs, db->trailing, d_list, n,
                                                             L.keys_in.p, L.idx_in.p);
   SWB_CUDA(cudaGetLastError());
   size_t tmp1 = 0, tmp2 = 0;
@@ -163,13 +242,13 @@ int build_layout(swb_db *db, Layout &L, const long long *d_list, long long n)
   SWB_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp.p, tb, L.nblk.p, L.pairblk.p,
                                          (int)(L.npairs + 1), st));
   // upper bound of the block total without a round trip: sum(max len) <= total residues
-  long long bound_res = d_list ? 0 : db->total_res;
-  if (d_list) bound_res = std::min<long long>(db->total_res, n * db->longest);
+  const long long bound_res = std::min<long long>(res_bound, n * db->longest);
+  L.res_bytes = bound_res;
   L.cap_blocks = (bound_res + 3 * L.npairs) / 4 + 1;
   SWB_TRY(L.blocks.reserve((size_t)L.cap_blocks));
   const long long threads = L.npairs * 32;
   swb_fill_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(
-      db->residues.p, db->offsets.p, db->trailing, d_list, L.keys_out.p, L.idx_out.p, n, L.npairs,
+      db->residues.p, offs, db->trailing, d_list, L.keys_out.p, L.idx_out.p, n, L.npairs,
       L.pairblk.p, L.blocks.p);
   SWB_CUDA(cudaGetLastError());
   return SWB_OK;
@@ -397,13 +476,16 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
   }
   else if (narrow)
   {
-    Layout *L = &db->all;
+    std::vector<Layout *> layouts;
     if (d_list)
     {
-      L = &db->tmp;
-      SWB_TRY(build_layout(db, *L, d_list, n));
+      SWB_CUDA(cudaStreamWaitEvent(st, db->ev_uploaded, 0));
+      SWB_TRY(build_layout(db, db->tmp, d_list, 0, n, db->total_res, st));
       launches += 5;
+      layouts.push_back(&db->tmp);
     }
+    else
+      layouts = db->chunks;
     // launch geometry: one CTA = 8 streams x G stages; as many CTAs per SM as shared memory
     // and registers allow
     const int threads = swb_scan_threads(shape->G);
@@ -416,48 +498,56 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     if (occ < 1) return SWB_ERR_INTERNAL;
     const int grid = db->sm_count * occ;
     const int nstreams = grid * SWB_STREAMS;
-    if (L->stream_pair_n != nstreams)
-    {
-      SWB_TRY(L->stream_pair.reserve((size_t)nstreams + 1));
-      swb_partition_kernel<<<(nstreams + 1 + 255) / 256, 256, 0, st>>>(L->pairblk.p, L->npairs,
-                                                                       nstreams, L->stream_pair.p);
-      SWB_CUDA(cudaGetLastError());
-      launches++;
-      L->stream_pair_n = nstreams;
-    }
     SWB_TRY(db->m16.reserve(SWB_MROWS * 32));
     SWB_TRY(db->qrow_off.reserve((size_t)rows_padded));
     SWB_CUDA(cudaMemcpyAsync(db->m16.p, tb.m16.data(), tb.m16.size() * sizeof(short),
                              cudaMemcpyHostToDevice, st));
     SWB_CUDA(cudaMemcpyAsync(db->qrow_off.p, tb.qrow.data(), tb.qrow.size() * sizeof(unsigned short),
                              cudaMemcpyHostToDevice, st));
+    long long max_blocks = 0;
+    for (Layout *L : layouts) max_blocks = std::max(max_blocks, L->cap_blocks);
     if (npass > 1)
     {
-      SWB_TRY(db->bndH.reserve((size_t)L->cap_blocks));
-      SWB_TRY(db->bndF.reserve((size_t)L->cap_blocks));
+      SWB_TRY(db->bndH.reserve((size_t)max_blocks));
+      SWB_TRY(db->bndF.reserve((size_t)max_blocks));
     }
-    SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * sizeof(u32), st));
-    ScanParams P;
-    P.blocks = L->blocks.p; P.pairblk = L->pairblk.p; P.stream_pair = L->stream_pair.p;
-    P.pair_scores = L->pair_scores.p; P.m16 = db->m16.p; P.qrow_off = db->qrow_off.p;
-    P.bndH = db->bndH.p; P.bndF = db->bndF.p;
-    P.nq = tb.nq; P.npass = npass;
+    SWB_TRY(db->requeue.reserve((size_t)n));
     const long long q = sc->gap_open_extend, r = sc->gap_extend;
     const unsigned nq16 = (unsigned)(unsigned short)enc16(-q, mode);
     const unsigned nr16 = (unsigned)(unsigned short)(short)(-r);
     const unsigned pad16 = (unsigned)(unsigned short)enc16(SWB_PAD_SCORE, mode);
-    P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
     const int limit = (mode != SWB_MODE_INT16 ? 2047 : 32767) - (int)std::max<long long>(tb.hi, 0);
     SWB_CUDA(cudaEventRecord(db->ev[0], st));
-    shape->fn<<<grid, threads, smem, st>>>(P);
-    SWB_CUDA(cudaGetLastError());
+    for (Layout *L : layouts)
+    {
+      if (L->n == 0) continue;
+      if (L->ev_ready) SWB_CUDA(cudaStreamWaitEvent(st, L->ev_ready, 0));
+      if (L->stream_pair_n != nstreams)
+      {
+        SWB_TRY(L->stream_pair.reserve((size_t)nstreams + 1));
+        swb_partition_kernel<<<(nstreams + 1 + 255) / 256, 256, 0, st>>>(L->pairblk.p, L->npairs,
+                                                                         nstreams, L->stream_pair.p);
+        SWB_CUDA(cudaGetLastError());
+        launches++;
+        L->stream_pair_n = nstreams;
+      }
+      SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * sizeof(u32), st));
+      ScanParams P;
+      P.blocks = L->blocks.p; P.pairblk = L->pairblk.p; P.stream_pair = L->stream_pair.p;
+      P.pair_scores = L->pair_scores.p; P.m16 = db->m16.p; P.qrow_off = db->qrow_off.p;
+      P.bndH = db->bndH.p; P.bndF = db->bndF.p;
+      P.nq = tb.nq; P.npass = npass;
+      P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
+      shape->fn<<<grid, threads, smem, st>>>(P);
+      SWB_CUDA(cudaGetLastError());
+      launches++;
+      swb_finish_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(
+          L->pair_scores.p, L->idx_out.p, L->n, L->first, limit, db->scores.p, db->requeue.p,
+          db->counters.p);
+      SWB_CUDA(cudaGetLastError());
+      launches++;
+    }
     SWB_CUDA(cudaEventRecord(db->ev[1], st));
-    launches++;
-    SWB_TRY(db->requeue.reserve((size_t)n));
-    swb_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-        L->pair_scores.p, L->idx_out.p, n, limit, db->scores.p, db->requeue.p, db->counters.p);
-    SWB_CUDA(cudaGetLastError());
-    launches++;
     unsigned long long h_nreq = 0;
     SWB_CUDA(cudaMemcpyAsync(&h_nreq, db->counters.p, sizeof h_nreq, cudaMemcpyDeviceToHost, st));
     SWB_CUDA(cudaStreamSynchronize(st));
@@ -469,6 +559,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
   }
   else
   {
+    SWB_CUDA(cudaStreamWaitEvent(st, db->ev_uploaded, 0));
     SWB_CUDA(cudaEventRecord(db->ev[0], st));
     SWB_CUDA(cudaEventRecord(db->ev[1], st));
     SWB_CUDA(cudaEventRecord(db->ev[2], st));
@@ -563,14 +654,20 @@ int swb_host_alloc(void **ptr, int64_t bytes)
   return SWB_OK;
 }
 
+int swb_trim(void)
+{
+  g_cache.trim();
+  return SWB_OK;
+}
+
 int swb_host_free(void *ptr)
 {
   if (ptr) SWB_CUDA(cudaFreeHost(ptr));
   return SWB_OK;
 }
 
-int swb_db_open(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
-                int trailing, void *stream, swb_db **out)
+static int open_impl(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
+                     int trailing, void *stream, swb_db **out, bool wait)
 {
   if (!out) return SWB_ERR_ARG;
   *out = nullptr;
@@ -589,70 +686,93 @@ int swb_db_open(int device, const uint8_t *residues, const int64_t *offsets, int
   SWB_TRY(swb_device_count(&ndev));
   if (device < 0 || device >= ndev) return SWB_ERR_NO_DEVICE;
   SWB_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  SWB_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
+  int cc_major = 0, cc_minor = 0, sm_count = 0;       // (cudaGetDeviceProperties costs milliseconds)
+  SWB_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  SWB_CUDA(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+  SWB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (cc_major != 10)
   {
-    g_cuda_error = std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+    g_cuda_error = std::string("device is sm_") + std::to_string(cc_major * 10 + cc_minor) +
                    ", the kernels are built for sm_100a only";
     return SWB_ERR_NO_DEVICE;
   }
   swb_db *db = new (std::nothrow) swb_db;
   if (!db) return SWB_ERR_NOMEM;
   db->device = device;
-  db->sm_count = prop.multiProcessorCount;
+  db->sm_count = sm_count;
   db->nseq = nseq; db->total_res = total; db->longest = longest; db->trailing = trailing;
-  int rc = SWB_OK;
-  do
+
+  // Pipeline chunks: contiguous subject ranges of about SWB_CHUNK_BYTES of residues each, so the
+  // upload of chunk c+1 overlaps the re-layout (and, once a search is issued, the scan) of chunk c.
+  long long chunk_bytes = 256LL << 20;
+  if (const char *env = getenv("SWB_CHUNK_BYTES"))      // test hook: force many small chunks
+    chunk_bytes = std::max<long long>(1, atoll(env));
+  std::vector<long long> cut;                       // chunk c covers subjects [cut[c], cut[c+1])
+  cut.push_back(0);
+  while (cut.back() < nseq)
   {
-#define SWB_STEP(x) if ((rc = (x)) != SWB_OK) break
+    const long long lo = cut.back();
+    const int64_t *e = std::upper_bound(offsets + lo + 1, offsets + nseq + 1, offsets[lo] + chunk_bytes);
+    long long hi = (long long)(e - offsets) - 1;     // last subject boundary within the byte budget
+    if (hi <= lo) hi = lo + 1;
+    if (nseq - hi < (hi - lo) / 4) hi = nseq;        // do not leave a sliver behind
+    cut.push_back(hi);
+  }
+
+  auto body = [&]() -> int {
     if (stream) db->stream = (cudaStream_t)stream;
     else
     {
-      SWB_STEP([&]() -> int { SWB_CUDA(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking)); return SWB_OK; }());
+      SWB_CUDA(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
       db->own_stream = true;
     }
-    SWB_STEP([&]() -> int {
-      for (int i = 0; i < 4; i++) SWB_CUDA(cudaEventCreate(&db->ev[i]));
-      return SWB_OK;
-    }());
-    SWB_STEP(db->residues.reserve((size_t)span + 16));
-    SWB_STEP(db->offsets.reserve((size_t)nseq + 1));
-    SWB_STEP([&]() -> int {
-      cudaStream_t st = db->stream;
-      SWB_CUDA(cudaEventRecord(db->ev[0], st));
-      // offsets are rebased so that residues[0] is the first byte uploaded
-      std::vector<long long> rebased;
-      const long long *src = (const long long *)offsets;
-      if (offsets[0] != 0)
-      {
-        rebased.resize((size_t)nseq + 1);
-        for (long long i = 0; i <= nseq; i++) rebased[(size_t)i] = offsets[i] - offsets[0];
-        src = rebased.data();
-      }
-      SWB_CUDA(cudaMemcpyAsync(db->offsets.p, src, ((size_t)nseq + 1) * sizeof(long long),
-                               cudaMemcpyHostToDevice, st));
-      if (span > 0)
-        SWB_CUDA(cudaMemcpyAsync(db->residues.p, residues + offsets[0], (size_t)span,
-                                 cudaMemcpyHostToDevice, st));
-      SWB_CUDA(cudaStreamSynchronize(st));     // rebased may go out of scope
-      SWB_CUDA(cudaEventRecord(db->ev[1], st));
-      return SWB_OK;
-    }());
-    SWB_STEP(build_layout(db, db->all, nullptr, nseq));
-    SWB_STEP([&]() -> int {
-      cudaStream_t st = db->stream;
-      SWB_CUDA(cudaEventRecord(db->ev[2], st));
-      SWB_CUDA(cudaStreamSynchronize(st));
-      float ms = 0;
-      SWB_CUDA(cudaEventElapsedTime(&ms, db->ev[0], db->ev[1]));
-      db->upload_ms = ms;
-      SWB_CUDA(cudaEventElapsedTime(&ms, db->ev[1], db->ev[2]));
-      db->layout_ms = ms;
-      return SWB_OK;
-    }());
-#undef SWB_STEP
-  } while (0);
+    SWB_CUDA(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
+    SWB_CUDA(cudaStreamCreateWithFlags(&db->layout_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) SWB_CUDA(cudaEventCreate(&db->ev[i]));
+    for (int i = 0; i < 3; i++) SWB_CUDA(cudaEventCreate(&db->ev_open[i]));
+    SWB_CUDA(cudaEventCreateWithFlags(&db->ev_uploaded, cudaEventDisableTiming));
+    SWB_TRY(db->residues.reserve((size_t)span + 16));
+    SWB_TRY(db->offsets.reserve((size_t)nseq + 1));
+    // offsets are rebased so that residues[0] is the first byte uploaded
+    std::vector<long long> rebased;
+    const long long *src = (const long long *)offsets;
+    if (offsets[0] != 0)
+    {
+      rebased.resize((size_t)nseq + 1);
+      for (long long i = 0; i <= nseq; i++) rebased[(size_t)i] = offsets[i] - offsets[0];
+      src = rebased.data();
+    }
+    SWB_CUDA(cudaEventRecord(db->ev_open[0], db->copy_stream));
+    SWB_CUDA(cudaMemcpyAsync(db->offsets.p, src, ((size_t)nseq + 1) * sizeof(long long),
+                             cudaMemcpyHostToDevice, db->copy_stream));
+    if (!rebased.empty()) SWB_CUDA(cudaStreamSynchronize(db->copy_stream));
+    for (size_t c = 0; c + 1 < cut.size(); c++)
+    {
+      Layout *L = new (std::nothrow) Layout;
+      if (!L) return SWB_ERR_NOMEM;
+      db->chunks.push_back(L);
+      const long long lo = cut[c], hi = cut[c + 1];
+      const long long b0 = offsets[lo] - offsets[0], b1 = offsets[hi] - offsets[0];
+      if (b1 > b0)
+        SWB_CUDA(cudaMemcpyAsync(db->residues.p + b0, residues + offsets[lo], (size_t)(b1 - b0),
+                                 cudaMemcpyHostToDevice, db->copy_stream));
+      SWB_CUDA(cudaEventCreateWithFlags(&L->ev_ready, cudaEventDisableTiming));
+      cudaEvent_t up;
+      SWB_CUDA(cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
+      SWB_CUDA(cudaEventRecord(up, db->copy_stream));
+      SWB_CUDA(cudaStreamWaitEvent(db->layout_stream, up, 0));
+      SWB_CUDA(cudaEventDestroy(up));             // released once the wait has consumed it
+      if (c == 0) SWB_CUDA(cudaEventRecord(db->ev_open[1], db->layout_stream));
+      SWB_TRY(build_layout(db, *L, nullptr, lo, hi - lo, b1 - b0, db->layout_stream));
+      SWB_CUDA(cudaEventRecord(L->ev_ready, db->layout_stream));
+    }
+    SWB_CUDA(cudaEventRecord(db->ev_uploaded, db->copy_stream));
+    SWB_CUDA(cudaEventRecord(db->ev_open[2], db->layout_stream));
+    if (db->chunks.empty()) SWB_CUDA(cudaEventRecord(db->ev_open[1], db->layout_stream));
+    if (wait) SWB_TRY(swb_db_wait(db));
+    return SWB_OK;
+  };
+  const int rc = body();
   if (rc != SWB_OK)
   {
     swb_db_close(db);
@@ -662,18 +782,58 @@ int swb_db_open(int device, const uint8_t *residues, const int64_t *offsets, int
   return SWB_OK;
 }
 
+int swb_db_open(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
+                int trailing, void *stream, swb_db **out)
+{
+  return open_impl(device, residues, offsets, nseq, trailing, stream, out, true);
+}
+
+int swb_db_open_async(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
+                      int trailing, void *stream, swb_db **out)
+{
+  return open_impl(device, residues, offsets, nseq, trailing, stream, out, false);
+}
+
+int swb_db_wait(swb_db *db)
+{
+  if (!db) return SWB_ERR_ARG;
+  SWB_CUDA(cudaSetDevice(db->device));
+  SWB_CUDA(cudaStreamSynchronize(db->copy_stream));
+  SWB_CUDA(cudaStreamSynchronize(db->layout_stream));
+  if (!db->opened_sync)
+  {
+    float ms = 0;
+    SWB_CUDA(cudaEventSynchronize(db->ev_open[2]));
+    SWB_CUDA(cudaEventElapsedTime(&ms, db->ev_open[0], db->ev_open[2]));
+    db->upload_ms = ms;                      // first byte sent .. last layout done (pipelined)
+    SWB_CUDA(cudaEventElapsedTime(&ms, db->ev_open[1], db->ev_open[2]));
+    db->layout_ms = ms;
+    db->opened_sync = true;
+  }
+  return SWB_OK;
+}
+
 int swb_db_close(swb_db *db)
 {
   if (!db) return SWB_OK;
   cudaSetDevice(db->device);
+  if (db->copy_stream) cudaStreamSynchronize(db->copy_stream);
+  if (db->layout_stream) cudaStreamSynchronize(db->layout_stream);
   if (db->stream) cudaStreamSynchronize(db->stream);
-  db->residues.release(); db->offsets.release(); db->all.release(); db->tmp.release();
+  db->residues.release(); db->offsets.release(); db->tmp.release();
+  for (Layout *L : db->chunks) { L->release(); delete L; }
+  db->chunks.clear();
   db->m16.release(); db->qrow_off.release(); db->matrix.release(); db->query.release();
   db->scores.release(); db->bestpos.release(); db->bestq.release(); db->requeue.release();
   db->list.release(); db->counters.release(); db->he.release(); db->bndH.release();
   db->bndF.release();
   for (int i = 0; i < 4; i++)
     if (db->ev[i]) cudaEventDestroy(db->ev[i]);
+  for (int i = 0; i < 3; i++)
+    if (db->ev_open[i]) cudaEventDestroy(db->ev_open[i]);
+  if (db->ev_uploaded) cudaEventDestroy(db->ev_uploaded);
+  if (db->copy_stream) cudaStreamDestroy(db->copy_stream);
+  if (db->layout_stream) cudaStreamDestroy(db->layout_stream);
   if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
   delete db;
   (void)cudaGetLastError();
@@ -776,6 +936,7 @@ int swb_set_mode(swb_db *db, int mode)
 int swb_db_open_ms(const swb_db *db, double *upload_ms, double *layout_ms)
 {
   if (!db) return SWB_ERR_ARG;
+  SWB_TRY(swb_db_wait(const_cast<swb_db *>(db)));
   if (upload_ms) *upload_ms = db->upload_ms;
   if (layout_ms) *layout_ms = db->layout_ms;
   return SWB_OK;

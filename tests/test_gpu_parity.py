@@ -221,3 +221,23 @@ def test_full_size_properties():
         sel2 = sel[:3000]
         assert np.array_equal(db.search_list(q, sc, sel2), a[sel2])
         assert a.min() >= 0
+
+
+def test_chunked_async_open(oracle, monkeypatch):
+    """The shard is uploaded, re-laid-out and scanned in pipeline chunks; force many small chunks
+    and the asynchronous open and check scores, list searches and counters are unchanged."""
+    q = synth.protein_query(200, seed=81)
+    residues, offsets = synth.protein_db(3000, query=q, seed=82, plant_every=11, max_len=800)
+    sc = Scoring(B62, 11, 1)
+    exp, _, _ = oracle.scan(residues, offsets, q, B62, 11, 1)
+    for chunk in ("50000", "1", "300000000"):
+        monkeypatch.setenv("SWB_CHUNK_BYTES", chunk)
+        for wait in (True, False):
+            with Database(residues, offsets, wait=wait) as db:
+                got = db.search(q, sc)
+                assert np.array_equal(got, exp), (chunk, wait)
+                assert db.last_counters["gpu_narrow"] + db.last_counters["gpu_requeued"] == 3000
+                sel = np.arange(0, 3000, 7)
+                assert np.array_equal(db.search_list(q, sc, sel), exp[sel])
+                db.set_shape(8, 8, 1)                     # multi-pass over chunks
+                assert np.array_equal(db.search(q, sc), exp)
