@@ -66,8 +66,6 @@ template <int MODE>
 __device__ __forceinline__ void swb_cell(u32 hd, u32 s, u32 &e, u32 &f, u32 &h, u32 &smax,
                                          const u32 negq, const u32 negr)
 {
-  const u32 r16_ = (0u - (negr & 0xffffu)) & 0x7fffu;
-  const u32 P_NEGR_FP = r16_ ? ((r16_ | (r16_ << 16)) | 0x80008000u) : 0u;  // -r as fp16 patterns
   if (MODE == SWB_MODE_INT16)
   {
     u32 t = __viaddmax_s16x2(hd, s, e);        // max(hd + s, e)
@@ -76,28 +74,6 @@ __device__ __forceinline__ void swb_cell(u32 hd, u32 s, u32 &e, u32 &f, u32 &h, 
     u32 hq = __vadd2(h, negq);                 // h - (open + extend)
     e = __viaddmax_s16x2(e, negr, hq);         // max(e - extend, h - open - extend)
     f = __viaddmax_s16x2(f, negr, hq);
-  }
-  else if (MODE == 2)
-  {
-    // experiment: 2-source max ops only (no VIMNMX3)
-    u32 a = swb_hadd2(hd, s);
-    u32 m = __vmaxs2(e, f);
-    h = __vimax_s16x2_relu(a, m);
-    smax = __vmaxs2(smax, h);
-    u32 hq = swb_hadd2(h, negq);
-    e = __viaddmax_s16x2_relu(e, negr, hq);
-    f = __viaddmax_s16x2_relu(f, negr, hq);
-  }
-  else if (MODE == 3)
-  {
-    // experiment: F through the FMA pipe (fp16-pattern add) + 2-source max
-    u32 a = swb_hadd2(hd, s);
-    h = __vimax3_s16x2_relu(a, e, f);
-    smax = __vmaxs2(smax, h);
-    u32 hq = swb_hadd2(h, negq);
-    e = __viaddmax_s16x2_relu(e, negr, hq);
-    u32 fr = swb_hadd2(f, P_NEGR_FP);
-    f = __vmaxs2(fr, hq);
   }
   else
   {
@@ -122,7 +98,8 @@ __host__ __device__ inline int swb_scan_threads(int G) { return SWB_STREAMS * G;
 __host__ __device__ inline size_t swb_scan_smem(int G, int nq)
 {
   const size_t warps = (size_t)(SWB_STREAMS * G) / 32;
-  return SWB_SMEM_HEADER + (size_t)(G + 1) * (nq + 2) * 128 + 2 * warps * SWB_STREAMS * SWB_XFER_BYTES;
+  return SWB_SMEM_HEADER + (size_t)(G + 1) * (nq + 2) * 128 +
+         (1 + 2 * warps) * SWB_STREAMS * SWB_XFER_BYTES;
 }
 
 // Thread geometry: a CTA runs 8 streams through G pipeline stages, thread = (stage g, stream k)
@@ -131,8 +108,9 @@ __host__ __device__ inline size_t swb_scan_smem(int G, int nq)
 // interleaved (16 B per stream in every 128-B table row) their LDS.128 requests hit one
 // 128-B line: no bank conflicts, whatever the query symbols are.  Stage g hands its bottom row to
 // stage g+1 by a shuffle over 8 lanes inside a warp and through a double-buffered shared-memory
-// mailbox between warps; one __syncthreads per step orders tables, mailboxes and ring reuse
-// (the ring has G+1 slots so that the slot being rebuilt was last read before the barrier).
+// mailbox between warps (stage 0 reads an all-zero mailbox); one __syncthreads per step orders
+// tables, mailboxes and ring reuse (the ring has G+1 slots so that the slot being rebuilt was
+// last read before the barrier).
 //
 // Table build: after the barrier of step t the CTA builds the tables of block t+1 (read from
 // step t+1 on).  Thread (g, k) fills column g & 3 of rows g>>2, g>>2 + G/4, ... of stream k's
@@ -141,31 +119,41 @@ __host__ __device__ inline size_t swb_scan_smem(int G, int nq)
 //
 // The DP tile itself runs unconditionally (threads outside their stream's block range chew on
 // stale tables; only their side effects are predicated off), which keeps the whole step one
-// straight-line region for the instruction scheduler.
-template <int G, int R, int MODE>
+// straight-line region for the instruction scheduler.  MP = the query needs more than one pass
+// (compiled out otherwise).  All shared-memory traffic goes through word/quad-word indices of
+// one typed array, so the compiler addresses it with 32-bit shared offsets.
+template <int G, int R, int MODE, bool MP>
 __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const ScanParams P)
 {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ uint4 smem4[];
+  u32 *const smem32 = (u32 *)smem4;
+  unsigned short *const smem16 = (unsigned short *)smem4;   // [33][SWB_MS_STRIDE] at offset 0
   constexpr int NSLOT = G + 1;
   constexpr int NWARP = SWB_STREAMS * G / 32;
   constexpr int RG = G / 4;                           // row groups of the table build
-  unsigned short *Ms = (unsigned short *)smem;       // [33][SWB_MS_STRIDE]
+  constexpr int NBJ = (32 + RG - 1) / RG;             // rows one thread may have to build
   const int tid = threadIdx.x;
   const int k = tid & 7;
   const int g = tid >> 3;
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int nq = P.nq;
-  const int slot_bytes = (nq + 2) * 128;
-  unsigned char *ring = smem + SWB_SMEM_HEADER;
-  unsigned char *xfer = ring + (size_t)NSLOT * slot_bytes;    // [2][NWARP][8] entries of 48 B
+  const u32 slot_bytes = (u32)(nq + 2) * 128u;
+  const u32 ring = SWB_SMEM_HEADER;                           // byte offsets into shared memory
+  const u32 ring_bytes = (u32)NSLOT * slot_bytes;
+  const u32 zbox = ring + ring_bytes;                         // 8 all-zero mailbox entries
+  const u32 xfer = zbox + SWB_STREAMS * SWB_XFER_BYTES;       // [2][NWARP][8] entries of 48 B
 
   for (int i = tid; i < SWB_MROWS * 32; i += blockDim.x)
-    Ms[(i >> 5) * SWB_MS_STRIDE + (i & 31)] = ((const unsigned short *)P.m16)[i];
-  // the pad row of every slot is written once; builds never touch it
+    smem16[(i >> 5) * SWB_MS_STRIDE + (i & 31)] = ((const unsigned short *)P.m16)[i];
+  // header rows start out flag-free; the pad row of every slot is written once and never rebuilt
   for (int i = tid; i < NSLOT * SWB_STREAMS; i += blockDim.x)
-    *(uint4 *)(ring + (i >> 3) * slot_bytes + (nq + 1) * 128 + (i & 7) * 16) =
-        make_uint4(P.padword, P.padword, P.padword, P.padword);
+  {
+    const u32 base = ring + (u32)(i >> 3) * slot_bytes + (u32)(i & 7) * 16u;
+    smem4[(base + (u32)nq * 128u) >> 4] = make_uint4(0, 0, 0, 0);
+    smem4[(base + (u32)(nq + 1) * 128u) >> 4] = make_uint4(P.padword, P.padword, P.padword, P.padword);
+  }
+  for (int i = tid; i < SWB_STREAMS * SWB_XFER_BYTES / 4; i += blockDim.x) smem32[(zbox >> 2) + i] = 0;
   __syncthreads();
 
   const int stream = blockIdx.x * SWB_STREAMS + k;
@@ -177,28 +165,38 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);   // every warp holds all 8 streams
   const int nsteps = nblk_max > 0 ? nblk_max + G - 1 : 0;
   const u32 negq = P.negq, negr = P.negr;
-  const bool first_quarter = (lane >> 3) == 0 && g > 0;
+  const bool first_quarter = (lane >> 3) == 0;
   const bool last_quarter = (lane >> 3) == 3 && g < G - 1;
-  const int bcol = g & 3;                              // table column this thread builds
-  const int brow = g >> 2;                             // first table row it builds
-  const u32 bshift = 8u * (u32)bcol;
-  unsigned char *const bdst = ring + k * 16 + bcol * 4;
+  const int brow = g >> 2;                             // first table row this thread builds
+  const u32 bshift = 8u * (u32)(g & 3);                // ... in table column g & 3
+  const u32 bdst = ring + (u32)k * 16u + (u32)(g & 3) * 4u + (u32)brow * 128u;
+  // mailbox addresses; the double buffer is walked by XOR-ing with the distance of the two halves
+  const u32 xhalf = (u32)NWARP * SWB_STREAMS * SWB_XFER_BYTES;
+  const u32 xin0 = warp == 0 ? zbox + (u32)k * SWB_XFER_BYTES
+                             : xfer + (u32)((warp - 1) * SWB_STREAMS + k) * SWB_XFER_BYTES;
+  const u32 xout0 = xfer + (u32)(warp * SWB_STREAMS + k) * SWB_XFER_BYTES;
+  const u32 xin_toggle = warp == 0 ? 0u : (xin0 ^ (xin0 + xhalf));   // a ^ b: x ^= toggle swaps a and b
+  const u32 xout_toggle = xout0 ^ (xout0 + xhalf);
 
-  // builds column bcol of stream k's table for the block word pair (x, y) into slot `slot`
-  auto build = [&](const uint2 blkw, const int slot) {
-    const u32 da = ((blkw.x >> bshift) & 63u) * SWB_MS_STRIDE;
-    const u32 db = ((blkw.y >> bshift) & 63u) * SWB_MS_STRIDE;
-    unsigned char *dst = bdst + slot * slot_bytes;
-    for (int s = brow; s < nq; s += RG)
-      *(u32 *)(dst + s * 128) = __byte_perm(Ms[da + s], Ms[db + s], 0x5410);
-    if (g == 0) *(u32 *)(dst + nq * 128) = (blkw.x >> 6) & 3u;
+  // builds column g & 3 of stream k's table for block words (x, y) at byte offset slot_off
+  auto build = [&](const uint2 blkw, const u32 slot_off) {
+    const u32 da = ((blkw.x >> bshift) & 63u) * SWB_MS_STRIDE + (u32)brow;
+    const u32 db = ((blkw.y >> bshift) & 63u) * SWB_MS_STRIDE + (u32)brow;
+    const u32 dst = (bdst + slot_off) >> 2;
+#pragma unroll
+    for (int j = 0; j < NBJ; j++)
+      if (brow + j * RG < nq)
+        smem32[dst + j * RG * 32] = __byte_perm(smem16[da + j * RG], smem16[db + j * RG], 0x5410);
+    if (g == 0) smem32[((ring + slot_off + (u32)nq * 128u) >> 2) + k * 4] = (blkw.x >> 6) & 3u;
   };
 
-  for (int pass = 0; pass < P.npass; pass++)
+  const int npass = MP ? P.npass : 1;
+  for (int pass = 0; pass < npass; pass++)
   {
     u32 rq[R];
 #pragma unroll
-    for (int i = 0; i < R; i++) rq[i] = (u32)P.qrow_off[(pass * G + g) * R + i] * 8u + (u32)k * 16u;
+    for (int i = 0; i < R; i++)
+      rq[i] = ring + (u32)P.qrow_off[(pass * G + g) * R + i] * 8u + (u32)k * 16u;
 
     u32 H[R], E[R];
 #pragma unroll
@@ -206,38 +204,40 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
     u32 smax = 0, dtop = 0;
     u32 ih0 = 0, ih1 = 0, ih2 = 0, ih3 = 0, if0 = 0, if1 = 0, if2 = 0, if3 = 0, is = 0;
     int pair_out = p0;
-    const bool feed = (pass > 0) && (g == 0);          // stage 0 reads the previous pass's bottom row
-    const bool spill = (pass + 1 < P.npass) && (g == G - 1);
+    const bool feed = MP && (pass > 0) && (g == 0);    // stage 0 reads the previous pass's bottom row
+    const bool spill = MP && (pass + 1 < npass) && (g == G - 1);
 
-    if (pass > 0) __syncthreads();                     // the previous pass is done with ring and mailboxes
+    if (MP && pass > 0) __syncthreads();               // the previous pass is done with ring and mailboxes
     uint2 nxt = make_uint2(0, 0);                      // block t + 1
     if (nblk > 0) build(blk[0], 0);
     if (nblk > 1) nxt = blk[1];
-    int wslot = 1;                                     // (t + 1) % NSLOT
-    int rslot = (NSLOT - g) % NSLOT;                   // (t - g) mod NSLOT, kept non-negative
+    const uint2 *pnext = blk + 2;
+    u32 woff = slot_bytes;                             // ((t + 1) % NSLOT) * slot_bytes
+    u32 roff = (u32)((NSLOT - g) % NSLOT) * slot_bytes;  // ((t - g) mod NSLOT) * slot_bytes
+    u32 xin = xin0 ^ xin_toggle;                       // the half written at step t - 1
+    u32 xout = xout0;
+    int b = -g;
 
     for (int t = 0; t < nsteps; t++)
     {
       __syncthreads();
       // ---- tables of block t + 1 (first read after the next barrier) ------------------------------
       const uint2 cur = nxt;
-      if (t + 2 < nblk) nxt = blk[t + 2];
-      if (t + 1 < nblk) build(cur, wslot);
+      if (t + 2 < nblk) nxt = *pnext;
+      pnext++;
+      if (t + 1 < nblk) build(cur, woff);
 
-      // ---- stage g works on block t - g ------------------------------------------------------------
-      const int b = t - g;
+      // ---- stage g works on block b = t - g ----------------------------------------------------------
       const bool active = b >= 0 && b < nblk;
-      const unsigned char *slot = ring + rslot * slot_bytes;
-      const u32 flags = *(const u32 *)(slot + nq * 128 + k * 16);
+      const u32 flags = smem32[((roff + ring + (u32)nq * 128u) >> 2) + k * 4];
       if (first_quarter)
       {
-        const unsigned char *x = xfer + ((((t + 1) & 1) * NWARP + (warp - 1)) * 8 + k) * SWB_XFER_BYTES;
-        const uint4 vh = *(const uint4 *)x, vf = *(const uint4 *)(x + 16);
+        const uint4 vh = smem4[xin >> 4], vf = smem4[(xin >> 4) + 1];
         ih0 = vh.x; ih1 = vh.y; ih2 = vh.z; ih3 = vh.w;
         if0 = vf.x; if1 = vf.y; if2 = vf.z; if3 = vf.w;
-        is = *(const u32 *)(x + 32);
+        is = smem32[(xin >> 2) + 8];
       }
-      if (feed && active)
+      if (MP && feed && active)
       {
         const uint4 vh = P.bndH[b0 + b], vf = P.bndF[b0 + b];
         ih0 = vh.x; ih1 = vh.y; ih2 = vh.z; ih3 = vh.w;
@@ -254,10 +254,11 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       u32 hup0 = ih0, hup1 = ih1, hup2 = ih2, hup3 = ih3;
       u32 f0 = if0, f1 = if1, f2 = if2, f3 = if3;
       u32 dg = dtop;
+      dtop = ih3;
 #pragma unroll
       for (int i = 0; i < R; i++)
       {
-        const uint4 sc = *(const uint4 *)(slot + rq[i]);
+        const uint4 sc = smem4[(rq[i] + roff) >> 4];
         u32 hd = dg, e = E[i], h;
         dg = H[i];
         swb_cell<MODE>(hd, sc.x, e, f0, h, smax, negq, negr); hd = hup0; hup0 = h;
@@ -267,8 +268,7 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
         H[i] = h;
         E[i] = e;
       }
-      dtop = ih3;
-      if (spill && active)
+      if (MP && spill && active)
       {
         P.bndH[b0 + b] = make_uint4(hup0, hup1, hup2, hup3);
         P.bndF[b0 + b] = make_uint4(f0, f1, f2, f3);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       if (g == G - 1 && active && (flags & SWB_FLAG_END))
       {
         u32 v = smax;
-        if (pass > 0) v = __vmaxs2(v, P.pair_scores[pair_out]);
+        if (MP && pass > 0) v = __vmaxs2(v, P.pair_scores[pair_out]);
         P.pair_scores[pair_out] = v;
         pair_out++;
       }
@@ -284,10 +284,9 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       // ---- hand the strip's bottom row to the next stage --------------------------------------------
       if (last_quarter)
       {
-        unsigned char *x = xfer + (((t & 1) * NWARP + warp) * 8 + k) * SWB_XFER_BYTES;
-        *(uint4 *)x = make_uint4(hup0, hup1, hup2, hup3);
-        *(uint4 *)(x + 16) = make_uint4(f0, f1, f2, f3);
-        *(u32 *)(x + 32) = smax;
+        smem4[xout >> 4] = make_uint4(hup0, hup1, hup2, hup3);
+        smem4[(xout >> 4) + 1] = make_uint4(f0, f1, f2, f3);
+        smem32[(xout >> 2) + 8] = smax;
       }
       ih0 = __shfl_up_sync(0xffffffffu, hup0, 8);
       ih1 = __shfl_up_sync(0xffffffffu, hup1, 8);
@@ -298,9 +297,11 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       if2 = __shfl_up_sync(0xffffffffu, f2, 8);
       if3 = __shfl_up_sync(0xffffffffu, f3, 8);
       is = __shfl_up_sync(0xffffffffu, smax, 8);
-      if (g == 0) { ih0 = ih1 = ih2 = ih3 = 0; if0 = if1 = if2 = if3 = 0; is = 0; }
-      wslot = wslot + 1 == NSLOT ? 0 : wslot + 1;
-      rslot = rslot + 1 == NSLOT ? 0 : rslot + 1;
+      woff = woff + slot_bytes == ring_bytes ? 0u : woff + slot_bytes;
+      roff = roff + slot_bytes == ring_bytes ? 0u : roff + slot_bytes;
+      xin ^= xin_toggle;
+      xout ^= xout_toggle;
+      b++;
     }
   }
 }

@@ -313,19 +313,17 @@ int prepare_tables(Tables &t, const unsigned char *query, long long qlen, const 
 
 // ---- kernel shapes -----------------------------------------------------------------------------
 typedef void (*scan_fn)(const ScanParams);
-struct ShapeEntry { int G, R, mode; scan_fn fn; };
+struct ShapeEntry { int G, R, mode; scan_fn fn, fn_mp; };     // single-pass / multi-pass builds
 
-#define SWB_SHAPE(G, R)                                           \
-  {G, R, SWB_MODE_INT16, swb_scan_kernel<G, R, SWB_MODE_INT16>},  \
-  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID>}
-#define SWB_SHAPE_X(G, R)                                         \
-  {G, R, SWB_MODE_INT16, swb_scan_kernel<G, R, SWB_MODE_INT16>},  \
-  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID>},\
-  {G, R, 2, swb_scan_kernel<G, R, 2>}, {G, R, 3, swb_scan_kernel<G, R, 3>}
+#define SWB_SHAPE(G, R)                                                                          \
+  {G, R, SWB_MODE_INT16, swb_scan_kernel<G, R, SWB_MODE_INT16, false>,                           \
+   swb_scan_kernel<G, R, SWB_MODE_INT16, true>},                                                 \
+  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID, false>,                         \
+   swb_scan_kernel<G, R, SWB_MODE_HYBRID, true>}
 
 const ShapeEntry g_shapes[] = {
     SWB_SHAPE(8, 8),   SWB_SHAPE(8, 13),  SWB_SHAPE(8, 16),  SWB_SHAPE(16, 12), SWB_SHAPE(16, 16),
-    SWB_SHAPE(16, 20), SWB_SHAPE_X(16, 24), SWB_SHAPE(32, 12), SWB_SHAPE(32, 16), SWB_SHAPE(32, 20),
+    SWB_SHAPE(16, 20), SWB_SHAPE(16, 24), SWB_SHAPE(32, 12), SWB_SHAPE(32, 16), SWB_SHAPE(32, 20),
     SWB_SHAPE(32, 24), SWB_SHAPE(32, 28), SWB_SHAPE(32, 32),
 };
 const int g_nshapes = (int)(sizeof(g_shapes) / sizeof(g_shapes[0]));
@@ -490,10 +488,11 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     // and registers allow
     const int threads = swb_scan_threads(shape->G);
     const size_t smem = swb_scan_smem(shape->G, tb.nq);
-    SWB_CUDA(cudaFuncSetAttribute((const void *)shape->fn,
+    const scan_fn fn = npass > 1 ? shape->fn_mp : shape->fn;
+    SWB_CUDA(cudaFuncSetAttribute((const void *)fn,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)shape->fn, threads,
+    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, threads,
                                                            smem));
     if (occ < 1) return SWB_ERR_INTERNAL;
     const int grid = db->sm_count * occ;
@@ -538,7 +537,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       P.bndH = db->bndH.p; P.bndF = db->bndF.p;
       P.nq = tb.nq; P.npass = npass;
       P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
-      shape->fn<<<grid, threads, smem, st>>>(P);
+      fn<<<grid, threads, smem, st>>>(P);
       SWB_CUDA(cudaGetLastError());
       launches++;
       swb_finish_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(
@@ -953,7 +952,7 @@ int swb_set_shape(swb_db *db, int G, int R, int lane_mode)
     for (int i = 0; i < g_nshapes; i++) found = found || (g_shapes[i].G == G && g_shapes[i].R == R);
     if (!found) return SWB_ERR_ARG;
   }
-  if (lane_mode < -1 || lane_mode > 3) return SWB_ERR_ARG;
+  if (lane_mode < -1 || lane_mode > 1) return SWB_ERR_ARG;
   db->force_G = G; db->force_R = R; db->force_mode = lane_mode;
   return SWB_OK;
 }
