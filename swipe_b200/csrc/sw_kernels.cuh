@@ -60,6 +60,40 @@ __device__ __forceinline__ u32 swb_hadd2(u32 a, u32 b)
   return r;
 }
 
+// Shared-memory access by 32-bit shared-window address (no generic-pointer arithmetic, no
+// alignment masks in the instruction stream).  The "memory" clobber keeps them ordered against
+// __syncthreads at the compiler level; ptxas schedules them like any other LDS/STS.
+__device__ __forceinline__ uint4 swb_lds128(u32 a)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ u32 swb_lds32(u32 a)
+{
+  u32 v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ u32 swb_lds16(u32 a)
+{
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void swb_sts128(u32 a, uint4 v)
+{
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void swb_sts32(u32 a, u32 v)
+{
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void swb_sts16(u32 a, unsigned short v)
+{
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
+}
+
 // One DP cell for both lanes.  hd = H(i-1,j-1), s = score word, e = E(i,j), f = F(i,j).
 // Produces h = H(i,j) and advances e -> E(i,j+1), f -> F(i+1,j); smax accumulates max H.
 template <int MODE>
@@ -126,8 +160,7 @@ template <int G, int R, int MODE, bool MP>
 __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const ScanParams P)
 {
   extern __shared__ uint4 smem4[];
-  u32 *const smem32 = (u32 *)smem4;
-  unsigned short *const smem16 = (unsigned short *)smem4;   // [33][SWB_MS_STRIDE] at offset 0
+  const u32 sbase = (u32)__cvta_generic_to_shared(smem4);     // staged score matrix at sbase
   constexpr int NSLOT = G + 1;
   constexpr int NWARP = SWB_STREAMS * G / 32;
   constexpr int RG = G / 4;                           // row groups of the table build
@@ -139,21 +172,21 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   const int warp = tid >> 5;
   const int nq = P.nq;
   const u32 slot_bytes = (u32)(nq + 2) * 128u;
-  const u32 ring = SWB_SMEM_HEADER;                           // byte offsets into shared memory
+  const u32 ring = sbase + SWB_SMEM_HEADER;                   // shared-window byte addresses
   const u32 ring_bytes = (u32)NSLOT * slot_bytes;
   const u32 zbox = ring + ring_bytes;                         // 8 all-zero mailbox entries
   const u32 xfer = zbox + SWB_STREAMS * SWB_XFER_BYTES;       // [2][NWARP][8] entries of 48 B
 
   for (int i = tid; i < SWB_MROWS * 32; i += blockDim.x)
-    smem16[(i >> 5) * SWB_MS_STRIDE + (i & 31)] = ((const unsigned short *)P.m16)[i];
+    swb_sts16(sbase + 2u * (u32)((i >> 5) * SWB_MS_STRIDE + (i & 31)), ((const unsigned short *)P.m16)[i]);
   // header rows start out flag-free; the pad row of every slot is written once and never rebuilt
   for (int i = tid; i < NSLOT * SWB_STREAMS; i += blockDim.x)
   {
     const u32 base = ring + (u32)(i >> 3) * slot_bytes + (u32)(i & 7) * 16u;
-    smem4[(base + (u32)nq * 128u) >> 4] = make_uint4(0, 0, 0, 0);
-    smem4[(base + (u32)(nq + 1) * 128u) >> 4] = make_uint4(P.padword, P.padword, P.padword, P.padword);
+    swb_sts128(base + (u32)nq * 128u, make_uint4(0, 0, 0, 0));
+    swb_sts128(base + (u32)(nq + 1) * 128u, make_uint4(P.padword, P.padword, P.padword, P.padword));
   }
-  for (int i = tid; i < SWB_STREAMS * SWB_XFER_BYTES / 4; i += blockDim.x) smem32[(zbox >> 2) + i] = 0;
+  for (int i = tid; i < SWB_STREAMS * SWB_XFER_BYTES / 4; i += blockDim.x) swb_sts32(zbox + 4u * i, 0);
   __syncthreads();
 
   const int stream = blockIdx.x * SWB_STREAMS + k;
@@ -170,24 +203,26 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   const int brow = g >> 2;                             // first table row this thread builds
   const u32 bshift = 8u * (u32)(g & 3);                // ... in table column g & 3
   const u32 bdst = ring + (u32)k * 16u + (u32)(g & 3) * 4u + (u32)brow * 128u;
-  // mailbox addresses; the double buffer is walked by XOR-ing with the distance of the two halves
+  const u32 bsrc = sbase + 2u * (u32)brow;
+  const u32 hdr = ring + (u32)nq * 128u + (u32)k * 16u;       // this stream's flag word in slot 0
+  // mailbox addresses; the double buffer is walked by XOR-ing with a ^ b of its two halves
   const u32 xhalf = (u32)NWARP * SWB_STREAMS * SWB_XFER_BYTES;
   const u32 xin0 = warp == 0 ? zbox + (u32)k * SWB_XFER_BYTES
                              : xfer + (u32)((warp - 1) * SWB_STREAMS + k) * SWB_XFER_BYTES;
   const u32 xout0 = xfer + (u32)(warp * SWB_STREAMS + k) * SWB_XFER_BYTES;
-  const u32 xin_toggle = warp == 0 ? 0u : (xin0 ^ (xin0 + xhalf));   // a ^ b: x ^= toggle swaps a and b
+  const u32 xin_toggle = warp == 0 ? 0u : (xin0 ^ (xin0 + xhalf));
   const u32 xout_toggle = xout0 ^ (xout0 + xhalf);
 
   // builds column g & 3 of stream k's table for block words (x, y) at byte offset slot_off
   auto build = [&](const uint2 blkw, const u32 slot_off) {
-    const u32 da = ((blkw.x >> bshift) & 63u) * SWB_MS_STRIDE + (u32)brow;
-    const u32 db = ((blkw.y >> bshift) & 63u) * SWB_MS_STRIDE + (u32)brow;
-    const u32 dst = (bdst + slot_off) >> 2;
+    const u32 da = bsrc + ((blkw.x >> bshift) & 63u) * (2u * SWB_MS_STRIDE);
+    const u32 db = bsrc + ((blkw.y >> bshift) & 63u) * (2u * SWB_MS_STRIDE);
+    const u32 dst = bdst + slot_off;
 #pragma unroll
     for (int j = 0; j < NBJ; j++)
       if (brow + j * RG < nq)
-        smem32[dst + j * RG * 32] = __byte_perm(smem16[da + j * RG], smem16[db + j * RG], 0x5410);
-    if (g == 0) smem32[((ring + slot_off + (u32)nq * 128u) >> 2) + k * 4] = (blkw.x >> 6) & 3u;
+        swb_sts32(dst + j * RG * 128, __byte_perm(swb_lds16(da + j * RG * 2), swb_lds16(db + j * RG * 2), 0x5410));
+    if (g == 0) swb_sts32(hdr + slot_off, (blkw.x >> 6) & 3u);
   };
 
   const int npass = MP ? P.npass : 1;
@@ -229,13 +264,13 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
 
       // ---- stage g works on block b = t - g ----------------------------------------------------------
       const bool active = b >= 0 && b < nblk;
-      const u32 flags = smem32[((roff + ring + (u32)nq * 128u) >> 2) + k * 4];
+      const u32 flags = swb_lds32(hdr + roff);
       if (first_quarter)
       {
-        const uint4 vh = smem4[xin >> 4], vf = smem4[(xin >> 4) + 1];
+        const uint4 vh = swb_lds128(xin), vf = swb_lds128(xin + 16);
         ih0 = vh.x; ih1 = vh.y; ih2 = vh.z; ih3 = vh.w;
         if0 = vf.x; if1 = vf.y; if2 = vf.z; if3 = vf.w;
-        is = smem32[(xin >> 2) + 8];
+        is = swb_lds32(xin + 32);
       }
       if (MP && feed && active)
       {
@@ -258,7 +293,7 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
 #pragma unroll
       for (int i = 0; i < R; i++)
       {
-        const uint4 sc = smem4[(rq[i] + roff) >> 4];
+        const uint4 sc = swb_lds128(rq[i] + roff);
         u32 hd = dg, e = E[i], h;
         dg = H[i];
         swb_cell<MODE>(hd, sc.x, e, f0, h, smax, negq, negr); hd = hup0; hup0 = h;
@@ -284,9 +319,9 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       // ---- hand the strip's bottom row to the next stage --------------------------------------------
       if (last_quarter)
       {
-        smem4[xout >> 4] = make_uint4(hup0, hup1, hup2, hup3);
-        smem4[(xout >> 4) + 1] = make_uint4(f0, f1, f2, f3);
-        smem32[(xout >> 2) + 8] = smax;
+        swb_sts128(xout, make_uint4(hup0, hup1, hup2, hup3));
+        swb_sts128(xout + 16, make_uint4(f0, f1, f2, f3));
+        swb_sts32(xout + 32, smax);
       }
       ih0 = __shfl_up_sync(0xffffffffu, hup0, 8);
       ih1 = __shfl_up_sync(0xffffffffu, hup1, 8);
