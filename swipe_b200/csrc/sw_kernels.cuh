@@ -94,6 +94,15 @@ __device__ __forceinline__ void swb_sts16(u32 a, unsigned short v)
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
 }
 
+// lo | hi << 16 as an integer multiply-add: runs on the FMA pipe, which has room, instead of a PRMT
+// on the ALU pipe, which is the bottleneck of the scan.
+__device__ __forceinline__ u32 swb_pack16(u32 lo, u32 hi)
+{
+  u32 r;
+  asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+  return r;
+}
+
 // One DP cell for both lanes.  hd = H(i-1,j-1), s = score word, e = E(i,j), f = F(i,j).
 // Produces h = H(i,j) and advances e -> E(i,j+1), f -> F(i+1,j); smax accumulates max H.
 template <int MODE>
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
 #pragma unroll
     for (int j = 0; j < NBJ; j++)
       if (brow + j * RG < nq)
-        swb_sts32(dst + j * RG * 128, __byte_perm(swb_lds16(da + j * RG * 2), swb_lds16(db + j * RG * 2), 0x5410));
+        swb_sts32(dst + j * RG * 128, swb_pack16(swb_lds16(da + j * RG * 2), swb_lds16(db + j * RG * 2)));
     if (g == 0) swb_sts32(hdr + slot_off, (blkw.x >> 6) & 3u);
   };
 

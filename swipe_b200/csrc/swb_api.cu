@@ -495,7 +495,18 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, threads,
                                                            smem));
     if (occ < 1) return SWB_ERR_INTERNAL;
-    const int grid = db->sm_count * occ;
+    if (const char *env = getenv("SWB_CTAS_PER_SM"))     // tuning hook: run below full occupancy
+      occ = std::max(1, std::min(occ, atoi(env)));
+    // More CTAs than resident slots: the hardware hands a fresh CTA to whichever SM finishes one,
+    // which evens out the warp scheduler's unfairness between co-resident CTAs (one persistent
+    // wave left SMs running 1-2 warps per scheduler towards the end of every launch).
+    int oversub = 2;
+    if (const char *env = getenv("SWB_OVERSUB")) oversub = std::max(1, atoi(env));
+    long long min_blocks = 0;
+    for (Layout *L : layouts) min_blocks = std::max(min_blocks, L->cap_blocks);
+    while (oversub > 1 && min_blocks / ((long long)db->sm_count * occ * oversub * SWB_STREAMS) < 40 * shape->G)
+      oversub--;                                   // keep streams much longer than the pipeline fill
+    const int grid = db->sm_count * occ * oversub;
     const int nstreams = grid * SWB_STREAMS;
     SWB_TRY(db->m16.reserve(SWB_MROWS * 32));
     SWB_TRY(db->qrow_off.reserve((size_t)rows_padded));
