@@ -36,12 +36,22 @@ typedef unsigned long long u64;
 
 enum { SWB_MODE_INT16 = 0, SWB_MODE_HYBRID = 1 };
 
-struct ScanParams
+// One re-laid-out chunk of the shard.  A launch covers one chunk (ScanParams::seg) or, once the
+// whole shard is resident, all of them at once: blockIdx.y picks the chunk from ScanParams::segs,
+// so the SMs run from one chunk into the next without a per-launch tail.
+struct ScanSeg
 {
   const uint2 *blocks;        // [total_blocks] 8 residues each: bytes 0-3 lane A cols 0-3, 4-7 lane B
   const long long *pairblk;   // [npairs+1] exclusive prefix of blocks per pair
   const int *stream_pair;     // [nstreams+1] first pair of every stream
   u32 *pair_scores;           // [npairs] packed lane maxima
+  long long bnd_base;         // first entry of this chunk in bndH / bndF
+};
+
+struct ScanParams
+{
+  ScanSeg seg;
+  const ScanSeg *segs;        // [gridDim.y] device array, or NULL: use seg
   const short *m16;           // [33][32] score of (subject code, table row) in the mode's encoding
   const unsigned short *qrow_off; // [npass*G*R] 16 * (table row of every query row)
   uint4 *bndH;                // [total_blocks] bottom H of a pass (only when npass > 1)
@@ -198,12 +208,15 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   for (int i = tid; i < SWB_STREAMS * SWB_XFER_BYTES / 4; i += blockDim.x) swb_sts32(zbox + 4u * i, 0);
   __syncthreads();
 
+  ScanSeg S = P.seg;
+  if (P.segs) S = P.segs[blockIdx.y];
   const int stream = blockIdx.x * SWB_STREAMS + k;
-  const int p0 = P.stream_pair[stream];
-  const int p1 = P.stream_pair[stream + 1];
-  const long long b0 = P.pairblk[p0];
-  const int nblk = (int)(P.pairblk[p1] - b0);
-  const uint2 *blk = P.blocks + b0;
+  const int p0 = S.stream_pair[stream];
+  const int p1 = S.stream_pair[stream + 1];
+  const long long b0 = S.pairblk[p0];
+  const int nblk = (int)(S.pairblk[p1] - b0);
+  const uint2 *blk = S.blocks + b0;
+  const long long bnd0 = S.bnd_base + b0;
   const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);   // every warp holds all 8 streams
   const int nsteps = nblk_max > 0 ? nblk_max + G - 1 : 0;
   const u32 negq = P.negq, negr = P.negr;
@@ -283,7 +296,7 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       }
       if (MP && feed && active)
       {
-        const uint4 vh = P.bndH[b0 + b], vf = P.bndF[b0 + b];
+        const uint4 vh = P.bndH[bnd0 + b], vf = P.bndF[bnd0 + b];
         ih0 = vh.x; ih1 = vh.y; ih2 = vh.z; ih3 = vh.w;
         if0 = vf.x; if1 = vf.y; if2 = vf.z; if3 = vf.w;
       }
@@ -314,14 +327,14 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       }
       if (MP && spill && active)
       {
-        P.bndH[b0 + b] = make_uint4(hup0, hup1, hup2, hup3);
-        P.bndF[b0 + b] = make_uint4(f0, f1, f2, f3);
+        P.bndH[bnd0 + b] = make_uint4(hup0, hup1, hup2, hup3);
+        P.bndF[bnd0 + b] = make_uint4(f0, f1, f2, f3);
       }
       if (g == G - 1 && active && (flags & SWB_FLAG_END))
       {
         u32 v = smax;
-        if (MP && pass > 0) v = __vmaxs2(v, P.pair_scores[pair_out]);
-        P.pair_scores[pair_out] = v;
+        if (MP && pass > 0) v = __vmaxs2(v, S.pair_scores[pair_out]);
+        S.pair_scores[pair_out] = v;
         pair_out++;
       }
 

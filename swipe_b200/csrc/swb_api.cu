@@ -195,6 +195,7 @@ struct swb_db
   DevBuf<unsigned long long> counters;       // [0] requeue count, [1..3] width counts
   DevBuf<unsigned char> he;
   DevBuf<uint4> bndH, bndF;
+  DevBuf<ScanSeg> segs;           // chunk table of a merged (whole-shard) scan launch
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   double upload_ms = 0, layout_ms = 0;
   int force_G = 0, force_R = 0, force_mode = -1;   // test hooks (swb_set_shape)
@@ -506,20 +507,33 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     for (Layout *L : layouts) min_blocks = std::max(min_blocks, L->cap_blocks);
     while (oversub > 1 && min_blocks / ((long long)db->sm_count * occ * oversub * SWB_STREAMS) < 40 * shape->G)
       oversub--;                                   // keep streams much longer than the pipeline fill
-    const int grid = db->sm_count * occ * oversub;
-    const int nstreams = grid * SWB_STREAMS;
     SWB_TRY(db->m16.reserve(SWB_MROWS * 32));
     SWB_TRY(db->qrow_off.reserve((size_t)rows_padded));
     SWB_CUDA(cudaMemcpyAsync(db->m16.p, tb.m16.data(), tb.m16.size() * sizeof(short),
                              cudaMemcpyHostToDevice, st));
     SWB_CUDA(cudaMemcpyAsync(db->qrow_off.p, tb.qrow.data(), tb.qrow.size() * sizeof(unsigned short),
                              cudaMemcpyHostToDevice, st));
-    long long max_blocks = 0;
-    for (Layout *L : layouts) max_blocks = std::max(max_blocks, L->cap_blocks);
+    // One launch per chunk while the shard is still arriving (upload / re-layout / scan overlap);
+    // one launch over all chunks (blockIdx.y = chunk) once every chunk is laid out, so that the SMs
+    // run from one chunk into the next and the ragged end of a launch is paid once per search.
+    bool merged = layouts.size() > 1;
+    if (const char *env = getenv("SWB_MERGE")) merged = merged && atoi(env) != 0;
+    for (Layout *L : layouts)
+      if (merged && L->ev_ready && cudaEventQuery(L->ev_ready) != cudaSuccess) merged = false;
+    (void)cudaGetLastError();
+    if (merged && !getenv("SWB_OVERSUB")) oversub = layouts.size() >= 4 ? 1 : oversub;
+    const int grid = db->sm_count * occ * oversub;
+    const int nstreams = grid * SWB_STREAMS;
+    long long max_blocks = 0, sum_blocks = 0;
+    for (Layout *L : layouts)
+    {
+      max_blocks = std::max(max_blocks, L->cap_blocks);
+      sum_blocks += L->cap_blocks;
+    }
     if (npass > 1)
     {
-      SWB_TRY(db->bndH.reserve((size_t)max_blocks));
-      SWB_TRY(db->bndF.reserve((size_t)max_blocks));
+      SWB_TRY(db->bndH.reserve((size_t)(merged ? sum_blocks : max_blocks)));
+      SWB_TRY(db->bndF.reserve((size_t)(merged ? sum_blocks : max_blocks)));
     }
     SWB_TRY(db->requeue.reserve((size_t)n));
     const long long q = sc->gap_open_extend, r = sc->gap_extend;
@@ -527,6 +541,13 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     const unsigned nr16 = (unsigned)(unsigned short)(short)(-r);
     const unsigned pad16 = (unsigned)(unsigned short)enc16(SWB_PAD_SCORE, mode);
     const int limit = (mode != SWB_MODE_INT16 ? 2047 : 32767) - (int)std::max<long long>(tb.hi, 0);
+    ScanParams P;
+    memset(&P, 0, sizeof P);
+    P.m16 = db->m16.p; P.qrow_off = db->qrow_off.p;
+    P.bndH = db->bndH.p; P.bndF = db->bndF.p;
+    P.nq = tb.nq; P.npass = npass;
+    P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
+    std::vector<ScanSeg> segs;
     SWB_CUDA(cudaEventRecord(db->ev[0], st));
     for (Layout *L : layouts)
     {
@@ -542,12 +563,16 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
         L->stream_pair_n = nstreams;
       }
       SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * sizeof(u32), st));
-      ScanParams P;
-      P.blocks = L->blocks.p; P.pairblk = L->pairblk.p; P.stream_pair = L->stream_pair.p;
-      P.pair_scores = L->pair_scores.p; P.m16 = db->m16.p; P.qrow_off = db->qrow_off.p;
-      P.bndH = db->bndH.p; P.bndF = db->bndF.p;
-      P.nq = tb.nq; P.npass = npass;
-      P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
+      ScanSeg S;
+      S.blocks = L->blocks.p; S.pairblk = L->pairblk.p; S.stream_pair = L->stream_pair.p;
+      S.pair_scores = L->pair_scores.p;
+      S.bnd_base = 0;
+      if (merged)
+      {
+        segs.push_back(S);                           // bnd_base is filled in below
+        continue;
+      }
+      P.seg = S;
       fn<<<grid, threads, smem, st>>>(P);
       SWB_CUDA(cudaGetLastError());
       launches++;
@@ -556,6 +581,34 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
           db->counters.p);
       SWB_CUDA(cudaGetLastError());
       launches++;
+    }
+    if (merged && !segs.empty())
+    {
+      long long base = 0;
+      size_t k = 0;
+      for (Layout *L : layouts)
+      {
+        if (L->n == 0) continue;
+        segs[k++].bnd_base = base;
+        base += L->cap_blocks;
+      }
+      SWB_TRY(db->segs.reserve(segs.size()));
+      SWB_CUDA(cudaMemcpyAsync(db->segs.p, segs.data(), segs.size() * sizeof(ScanSeg),
+                               cudaMemcpyHostToDevice, st));
+      P.seg = segs[0];
+      P.segs = db->segs.p;
+      fn<<<dim3((unsigned)grid, (unsigned)segs.size()), threads, smem, st>>>(P);
+      SWB_CUDA(cudaGetLastError());
+      launches++;
+      for (Layout *L : layouts)
+      {
+        if (L->n == 0) continue;
+        swb_finish_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(
+            L->pair_scores.p, L->idx_out.p, L->n, L->first, limit, db->scores.p, db->requeue.p,
+            db->counters.p);
+        SWB_CUDA(cudaGetLastError());
+        launches++;
+      }
     }
     SWB_CUDA(cudaEventRecord(db->ev[1], st));
     unsigned long long h_nreq = 0;
@@ -836,7 +889,7 @@ int swb_db_close(swb_db *db)
   db->m16.release(); db->qrow_off.release(); db->matrix.release(); db->query.release();
   db->scores.release(); db->bestpos.release(); db->bestq.release(); db->requeue.release();
   db->list.release(); db->counters.release(); db->he.release(); db->bndH.release();
-  db->bndF.release();
+  db->bndF.release(); db->segs.release();
   for (int i = 0; i < 4; i++)
     if (db->ev[i]) cudaEventDestroy(db->ev[i]);
   for (int i = 0; i < 3; i++)

@@ -230,8 +230,9 @@ def test_chunked_async_open(oracle, monkeypatch):
     residues, offsets = synth.protein_db(3000, query=q, seed=82, plant_every=11, max_len=800)
     sc = Scoring(B62, 11, 1)
     exp, _, _ = oracle.scan(residues, offsets, q, B62, 11, 1)
-    for chunk in ("50000", "1", "300000000"):
+    for chunk, merge in (("50000", "1"), ("50000", "0"), ("1", "1"), ("300000000", "1")):
         monkeypatch.setenv("SWB_CHUNK_BYTES", chunk)
+        monkeypatch.setenv("SWB_MERGE", merge)     # 1: one launch over all resident chunks
         for wait in (True, False):
             with Database(residues, offsets, wait=wait) as db:
                 got = db.search(q, sc)
