@@ -516,7 +516,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     // One launch per chunk while the shard is still arriving (upload / re-layout / scan overlap);
     // one launch over all chunks (blockIdx.y = chunk) once every chunk is laid out, so that the SMs
     // run from one chunk into the next and the ragged end of a launch is paid once per search.
-    bool merged = layouts.size() > 1;
+    bool merged = layouts.size() > 1 && layouts.size() <= 65535;   // gridDim.y limit
     if (const char *env = getenv("SWB_MERGE")) merged = merged && atoi(env) != 0;
     for (Layout *L : layouts)
       if (merged && L->ev_ready && cudaEventQuery(L->ev_ready) != cudaSuccess) merged = false;
