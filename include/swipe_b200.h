@@ -48,7 +48,8 @@ typedef enum swb_status
   SWB_ERR_CUDA = -3,      /* a CUDA runtime call failed; swb_last_cuda_error() has the text */
   SWB_ERR_NOMEM = -4,
   SWB_ERR_RANGE = -5,     /* scoring parameters outside what the kernels represent exactly */
-  SWB_ERR_INTERNAL = -6
+  SWB_ERR_INTERNAL = -6,
+  SWB_ERR_IO = -7         /* a database file is missing, truncated or corrupt; swb_blastdb_error() */
 } swb_status;
 
 /* Scoring parameters, exactly the values the reference hands its kernels.
@@ -121,6 +122,41 @@ int swb_db_open_async(int device, const uint8_t *residues, const int64_t *offset
 int swb_db_wait(swb_db *db);
 int swb_db_close(swb_db *db);
 int swb_db_info(const swb_db *db, int64_t *nseq, int64_t *total_residues, int64_t *longest);
+
+/* ---- BLAST database files ------------------------------------------------------------------
+ * Host-side reader of the version-4 BLAST databases the reference searches (db_open,
+ * database.cc:406-608, :775-925): basename.pin/.psq/.phr (protein) or .nin/.nsq/.nhr
+ * (nucleotide), optionally behind a .pal/.nal alias file listing several volumes (DBLIST) and a
+ * membership mask (OIDLIST + MEMB_BIT).  Global sequence numbers run through the volumes in order
+ * (seqno_volume, database.cc:637-660).  Files are memory-mapped; nothing is decoded until asked.
+ */
+typedef struct swb_blastdb swb_blastdb;
+int swb_blastdb_open(const char *basename, int nucleotide, swb_blastdb **out);
+int swb_blastdb_close(swb_blastdb *b);
+const char *swb_blastdb_error(void);   /* text of the last open failure on this thread */
+int swb_blastdb_info(const swb_blastdb *b, int64_t *nseq, int64_t *symbols, int64_t *longest,
+                     int *volumes);
+const char *swb_blastdb_title(const swb_blastdb *b);
+const char *swb_blastdb_date(const swb_blastdb *b);
+/* length in residues / nucleotides (database.cc:1246-1261), or a negative status */
+int64_t swb_blastdb_seqlen(const swb_blastdb *b, int64_t seqno);
+/* one sequence as symbol codes, as db_getsequence returns it (database.cc:1237-1353): protein
+ * bytes as stored; nucleotides as 4-bit codes with ambiguity runs applied, reverse-complemented
+ * when strand != 0.  *len receives the length even when cap is too small (SWB_ERR_RANGE).     */
+int swb_blastdb_sequence(const swb_blastdb *b, int64_t seqno, int strand, uint8_t *buf,
+                         int64_t cap, int64_t *len);
+/* the raw ASN.1 defline bytes (db_getheader, database.cc:1403-1413); points into the mapping   */
+int swb_blastdb_header(const swb_blastdb *b, int64_t seqno, const uint8_t **data, int64_t *len);
+/* 1 when the sequence passes the alias file's membership mask (db_check_msk, database.cc:687-706) */
+int swb_blastdb_included(const swb_blastdb *b, int64_t seqno);
+
+/* Uploads sequences [first, first + count) (count < 0: to the end) as one shard.  Protein volumes
+ * are copied as they lie in the .psq; nucleotide volumes are copied packed (4 bases per byte +
+ * ambiguity tables) and unpacked ON THE DEVICE to the 4-bit codes db_getsequence produces.  Subject
+ * i of the shard is global sequence first + i.  async != 0 behaves like swb_db_open_async (the
+ * swb_blastdb must stay open until swb_db_wait or the first search returns).                    */
+int swb_db_open_blast(int device, const swb_blastdb *b, int64_t first, int64_t count, int async,
+                      void *stream, swb_db **db);
 
 /* ---- the hot path ------------------------------------------------------------------------
  * swb_search: what search_chunk's cascade (swipe.cc:1416-1594) yields for every subject of the

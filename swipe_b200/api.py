@@ -9,13 +9,16 @@ from . import build as _build
 _LIB = None
 
 STATUS = {0: "SWB_OK", -1: "SWB_ERR_ARG", -2: "SWB_ERR_NO_DEVICE", -3: "SWB_ERR_CUDA",
-          -4: "SWB_ERR_NOMEM", -5: "SWB_ERR_RANGE", -6: "SWB_ERR_INTERNAL"}
+          -4: "SWB_ERR_NOMEM", -5: "SWB_ERR_RANGE", -6: "SWB_ERR_INTERNAL", -7: "SWB_ERR_IO"}
 
 # every symbol include/swipe_b200.h declares (tests check the library exports all of them)
 EXPORTS = ["swb_abi_version", "swb_strerror", "swb_last_cuda_error", "swb_device_count",
            "swb_host_alloc", "swb_host_free", "swb_db_open", "swb_db_close", "swb_db_info",
            "swb_search", "swb_search_list", "swb_search_end", "swb_topk_merge", "swb_set_mode",
-           "swb_db_open_ms", "swb_set_shape", "swb_db_open_async", "swb_db_wait", "swb_trim"]
+           "swb_db_open_ms", "swb_set_shape", "swb_db_open_async", "swb_db_wait", "swb_trim",
+           "swb_blastdb_open", "swb_blastdb_close", "swb_blastdb_error", "swb_blastdb_info",
+           "swb_blastdb_title", "swb_blastdb_date", "swb_blastdb_seqlen", "swb_blastdb_sequence",
+           "swb_blastdb_header", "swb_blastdb_included", "swb_db_open_blast"]
 
 
 class SwbError(RuntimeError):
@@ -84,6 +87,24 @@ def load_library():
                  "swb_db_close", "swb_db_info", "swb_search", "swb_search_list", "swb_search_end",
                  "swb_set_mode", "swb_db_open_ms", "swb_set_shape", "swb_db_open_async", "swb_db_wait"):
         getattr(lib, name).restype = C.c_int
+    lib.swb_blastdb_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.swb_blastdb_close.argtypes = [C.c_void_p]
+    lib.swb_blastdb_error.restype = C.c_char_p
+    lib.swb_blastdb_info.argtypes = [C.c_void_p, p64, p64, p64, C.POINTER(C.c_int)]
+    lib.swb_blastdb_title.restype = C.c_char_p
+    lib.swb_blastdb_title.argtypes = [C.c_void_p]
+    lib.swb_blastdb_date.restype = C.c_char_p
+    lib.swb_blastdb_date.argtypes = [C.c_void_p]
+    lib.swb_blastdb_seqlen.restype = C.c_int64
+    lib.swb_blastdb_seqlen.argtypes = [C.c_void_p, C.c_int64]
+    lib.swb_blastdb_sequence.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, p64]
+    lib.swb_blastdb_header.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), p64]
+    lib.swb_blastdb_included.argtypes = [C.c_void_p, C.c_int64]
+    lib.swb_db_open_blast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
+                                      C.POINTER(C.c_void_p)]
+    for name in ("swb_blastdb_open", "swb_blastdb_close", "swb_blastdb_info", "swb_blastdb_sequence",
+                 "swb_blastdb_header", "swb_blastdb_included", "swb_db_open_blast"):
+        getattr(lib, name).restype = C.c_int
     _LIB = lib
     return lib
 
@@ -95,6 +116,8 @@ def _check(rc):
         cuda = lib.swb_last_cuda_error().decode()
         if rc in (-2, -3, -4) and cuda:
             detail += " [" + cuda + "]"
+        if rc == -7:
+            detail += " [" + lib.swb_blastdb_error().decode() + "]"
         raise SwbError(rc, detail)
 
 
@@ -155,8 +178,79 @@ def _u8(a):
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
+class BlastDB:
+    """A BLAST version-4 database opened by the library's own reader (swb_blastdb)."""
+
+    def __init__(self, basename, nucleotide=False):
+        lib = load_library()
+        self._lib = lib
+        self._h = C.c_void_p()
+        _check(lib.swb_blastdb_open(os.fsencode(basename), int(bool(nucleotide)), C.byref(self._h)))
+        a, b, c, v = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        _check(lib.swb_blastdb_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(v)))
+        self.nseq, self.symbols, self.longest, self.volumes = a.value, b.value, c.value, v.value
+        self.nucleotide = bool(nucleotide)
+        self.title = lib.swb_blastdb_title(self._h).decode()
+        self.date = lib.swb_blastdb_date(self._h).decode()
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._lib.swb_blastdb_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seqlen(self, seqno):
+        n = self._lib.swb_blastdb_seqlen(self._h, int(seqno))
+        if n < 0:
+            _check(int(n))
+        return int(n)
+
+    def sequence(self, seqno, strand=0):
+        n = self.seqlen(seqno)
+        buf = np.empty(max(n, 1), dtype=np.uint8)
+        got = C.c_int64()
+        _check(self._lib.swb_blastdb_sequence(self._h, int(seqno), int(strand), buf.ctypes.data, n,
+                                              C.byref(got)))
+        return buf[:got.value].copy()
+
+    def header(self, seqno):
+        ptr, n = C.c_void_p(), C.c_int64()
+        _check(self._lib.swb_blastdb_header(self._h, int(seqno), C.byref(ptr), C.byref(n)))
+        return C.string_at(ptr.value, n.value) if n.value else b""
+
+    def included(self, seqno):
+        return bool(self._lib.swb_blastdb_included(self._h, int(seqno)))
+
+    def upload(self, device=0, first=0, count=-1, stream=None, wait=True):
+        """The shard [first, first+count) resident on one GPU (swb_db_open_blast)."""
+        return Database._from_blast(self, device, first, count, stream, wait)
+
+
 class Database:
     """One database shard resident on one GPU (swb_db)."""
+
+    @classmethod
+    def _from_blast(cls, bdb, device, first, count, stream, wait):
+        self = cls.__new__(cls)
+        self._lib = bdb._lib
+        self._bdb = bdb                       # keeps the mappings alive for an asynchronous open
+        self._h = C.c_void_p()
+        _check(self._lib.swb_db_open_blast(int(device), bdb._h, int(first), int(count), int(not wait),
+                                           C.c_void_p(stream or 0), C.byref(self._h)))
+        self.nseq = self.info()["nseq"]
+        self.last_counters = None
+        return self
 
     def __init__(self, residues, offsets, device=0, trailing=0, stream=None, wait=True):
         lib = load_library()

@@ -104,6 +104,15 @@ __device__ __forceinline__ void swb_sts16(u32 a, unsigned short v)
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
 }
 
+// database blocks are read-only for the kernel's lifetime: non-coherent global loads (the chunk
+// table is read through a generic pointer, so the compiler cannot infer the state space itself)
+__device__ __forceinline__ uint2 swb_ldg_blk(const uint2 *p)
+{
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(__cvta_generic_to_global(p)));
+  return v;
+}
+
 // lo | hi << 16 as an integer multiply-add: runs on the FMA pipe, which has room, instead of a PRMT
 // on the ALU pipe, which is the bottleneck of the scan.
 __device__ __forceinline__ u32 swb_pack16(u32 lo, u32 hi)
@@ -266,8 +275,8 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
 
     if (MP && pass > 0) __syncthreads();               // the previous pass is done with ring and mailboxes
     uint2 nxt = make_uint2(0, 0);                      // block t + 1
-    if (nblk > 0) build(blk[0], 0);
-    if (nblk > 1) nxt = blk[1];
+    if (nblk > 0) build(swb_ldg_blk(blk), 0);
+    if (nblk > 1) nxt = swb_ldg_blk(blk + 1);
     const uint2 *pnext = blk + 2;
     u32 woff = slot_bytes;                             // ((t + 1) % NSLOT) * slot_bytes
     u32 roff = (u32)((NSLOT - g) % NSLOT) * slot_bytes;  // ((t - g) mod NSLOT) * slot_bytes
@@ -280,7 +289,7 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       __syncthreads();
       // ---- tables of block t + 1 (first read after the next barrier) ------------------------------
       const uint2 cur = nxt;
-      if (t + 2 < nblk) nxt = *pnext;
+      if (t + 2 < nblk) nxt = swb_ldg_blk(pnext);
       pnext++;
       if (t + 1 < nblk) build(cur, woff);
 
@@ -431,6 +440,71 @@ __global__ void __launch_bounds__(128) swb_wide_kernel(const WideParams P)
   }
   P.scores[item] = (long long)best;
   if (END) { P.bestpos[item] = bd; P.bestq[item] = bq; }
+}
+
+// ---- nucleotide ingest ---------------------------------------------------------------------------
+// One warp per subject: unpack the .nsq record (4 bases per byte, most significant pair first; the
+// last byte carries the remaining len % 4 bases) to the 4-bit one-hot codes A=1 C=2 G=4 T=8 and
+// patch in the ambiguity runs that follow the packed bases -- what db_getsequence does per pull
+// on the host (database.cc:1257-1323), done once per shard here.  Table entries are big-endian:
+// 32-bit {code:4, run-1:4, offset:24}, or 64-bit {code:4, run-1:12, offset:48} when bit 31 of
+// the leading count word is set.
+__device__ __forceinline__ u32 swb_be32(const unsigned char *p)
+{
+  return ((u32)p[0] << 24) | ((u32)p[1] << 16) | ((u32)p[2] << 8) | (u32)p[3];
+}
+
+__global__ void swb_nt_decode_kernel(const unsigned char *packed, const long long *pk_start,
+                                     const u32 *pk_len, const long long *offsets,
+                                     unsigned char *residues, long long first, long long n)
+{
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const long long s = first + w;
+  const unsigned char *src = packed + pk_start[s];
+  unsigned char *dst = residues + offsets[s];
+  const long long len = offsets[s + 1] - offsets[s];
+  const long long nbytes = (len + 3) >> 2;
+  const bool aligned = (((unsigned long long)dst) & 3ull) == 0;
+  for (long long j = lane; j < nbytes; j += 32)
+  {
+    const u32 b = src[j];
+    const u32 word = (1u << ((b >> 6) & 3)) | ((1u << ((b >> 4) & 3)) << 8) |
+                     ((1u << ((b >> 2) & 3)) << 16) | ((1u << (b & 3)) << 24);
+    if (aligned && 4 * j + 4 <= len)
+      *(u32 *)(dst + 4 * j) = word;
+    else
+      for (int c = 0; c < 4; c++)
+        if (4 * j + c < len) dst[4 * j + c] = (unsigned char)(word >> (8 * c));
+  }
+  const long long abytes = pk_start[s + 1] - pk_start[s] - (long long)pk_len[s];
+  if (abytes < 4) return;
+  __syncwarp();
+  const unsigned char *amb = src + pk_len[s];
+  const u32 head = swb_be32(amb);
+  if (head >> 31)
+  {
+    const long long entries = (abytes - 4) >> 3;
+    for (long long k = lane; k < entries; k += 32)
+    {
+      const u64 e = ((u64)swb_be32(amb + 4 + 8 * k) << 32) | swb_be32(amb + 8 + 8 * k);
+      const unsigned char code = (unsigned char)(e >> 60);
+      const long long run = (long long)((e >> 48) & 0xfff) + 1, off = (long long)(e & 0x0000ffffffffffffULL);
+      for (long long r = 0; r < run && off + r < len; r++) dst[off + r] = code;
+    }
+  }
+  else
+  {
+    const long long entries = (abytes - 4) >> 2;
+    for (long long k = lane; k < entries; k += 32)
+    {
+      const u32 e = swb_be32(amb + 4 + 4 * k);
+      const unsigned char code = (unsigned char)(e >> 28);
+      const long long run = (long long)((e >> 24) & 0xf) + 1, off = (long long)(e & 0x00ffffffu);
+      for (long long r = 0; r < run && off + r < len; r++) dst[off + r] = code;
+    }
+  }
 }
 
 // ---- layout kernels ------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 //   hits_enter ........................ hits.cc:163-222      -> swb_topk_merge
 #include "../../include/swipe_b200.h"
 #include "sw_kernels.cuh"
+#include "swb_blastdb.h"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -180,6 +181,9 @@ struct swb_db
   int mode = 0;
   DevBuf<unsigned char> residues;
   DevBuf<long long> offsets;
+  DevBuf<unsigned char> packed;        // .nsq bytes as uploaded (nucleotide databases only)
+  DevBuf<long long> pk_start;          // [nseq+1] start of every subject's record in packed
+  DevBuf<u32> pk_len;                  // [nseq] bytes of packed bases in the record (rest: ambiguity table)
   std::vector<Layout *> chunks;   // the whole shard, cut into upload/layout/scan pipeline chunks
   Layout tmp;      // ad-hoc list layouts
   cudaStream_t copy_stream = nullptr, layout_stream = nullptr;
@@ -688,6 +692,7 @@ const char *swb_strerror(int status)
     case SWB_ERR_NOMEM: return "out of device or host memory";
     case SWB_ERR_RANGE: return "scoring parameters out of range";
     case SWB_ERR_INTERNAL: return "internal error";
+    case SWB_ERR_IO: return "database file missing, truncated or corrupt";
     default: return "unknown status";
   }
 }
@@ -729,22 +734,32 @@ int swb_host_free(void *ptr)
   return SWB_OK;
 }
 
-static int open_impl(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
-                     int trailing, void *stream, swb_db **out, bool wait)
+// Where the subjects of a shard come from.  `offsets` are byte offsets of the (decoded) residues
+// in the device residue buffer; `extents` name the host memory holding contiguous runs of subjects:
+// raw symbol bytes (copied as they are) or .nsq records (copied to the packed buffer and decoded on
+// the device by swb_nt_decode_kernel).
+struct Extent
 {
-  if (!out) return SWB_ERR_ARG;
-  *out = nullptr;
-  if (nseq < 0 || !offsets || trailing < 0 || trailing > 1 || nseq > 0x7ffffff0LL) return SWB_ERR_ARG;
-  const long long span = offsets[nseq] - offsets[0];
-  if (span < 0 || (span > 0 && !residues)) return SWB_ERR_ARG;
+  long long s0, s1;            // subjects [s0, s1)
+  const uint8_t *src;          // host address of the first byte of subject s0 (its record, if nsq)
+};
+struct OpenSrc
+{
+  long long nseq = 0;
+  int trailing = 0;
+  const long long *offsets = nullptr;     // [nseq+1], offsets[0] == 0
+  std::vector<long long> own_offsets;
   long long total = 0, longest = 0;
-  for (long long i = 0; i < nseq; i++)
-  {
-    const long long len = offsets[i + 1] - offsets[i] - trailing;
-    if (len < 0 || len > 0x7fffffffLL) return SWB_ERR_ARG;
-    total += len;
-    longest = std::max(longest, len);
-  }
+  bool nsq = false;
+  std::vector<long long> pk_start;        // [nseq+1] record offsets in the packed buffer (nsq)
+  std::vector<u32> pk_len;                // [nseq]
+  std::vector<Extent> extents;
+};
+
+static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wait)
+{
+  const long long nseq = S.nseq;
+  const long long *offsets = S.offsets;
   int ndev = 0;
   SWB_TRY(swb_device_count(&ndev));
   if (device < 0 || device >= ndev) return SWB_ERR_NO_DEVICE;
@@ -763,7 +778,7 @@ static int open_impl(int device, const uint8_t *residues, const int64_t *offsets
   if (!db) return SWB_ERR_NOMEM;
   db->device = device;
   db->sm_count = sm_count;
-  db->nseq = nseq; db->total_res = total; db->longest = longest; db->trailing = trailing;
+  db->nseq = nseq; db->total_res = S.total; db->longest = S.longest; db->trailing = S.trailing;
 
   // Pipeline chunks: contiguous subject ranges of about SWB_CHUNK_BYTES of residues each, so the
   // upload of chunk c+1 overlaps the re-layout (and, once a search is issued, the scan) of chunk c.
@@ -775,7 +790,7 @@ static int open_impl(int device, const uint8_t *residues, const int64_t *offsets
   while (cut.back() < nseq)
   {
     const long long lo = cut.back();
-    const int64_t *e = std::upper_bound(offsets + lo + 1, offsets + nseq + 1, offsets[lo] + chunk_bytes);
+    const long long *e = std::upper_bound(offsets + lo + 1, offsets + nseq + 1, offsets[lo] + chunk_bytes);
     long long hi = (long long)(e - offsets) - 1;     // last subject boundary within the byte budget
     if (hi <= lo) hi = lo + 1;
     if (nseq - hi < (hi - lo) / 4) hi = nseq;        // do not leave a sliver behind
@@ -794,31 +809,45 @@ static int open_impl(int device, const uint8_t *residues, const int64_t *offsets
     for (int i = 0; i < 4; i++) SWB_CUDA(cudaEventCreate(&db->ev[i]));
     for (int i = 0; i < 3; i++) SWB_CUDA(cudaEventCreate(&db->ev_open[i]));
     SWB_CUDA(cudaEventCreateWithFlags(&db->ev_uploaded, cudaEventDisableTiming));
-    SWB_TRY(db->residues.reserve((size_t)span + 16));
+    SWB_TRY(db->residues.reserve((size_t)offsets[nseq] + 16));
     SWB_TRY(db->offsets.reserve((size_t)nseq + 1));
-    // offsets are rebased so that residues[0] is the first byte uploaded
-    std::vector<long long> rebased;
-    const long long *src = (const long long *)offsets;
-    if (offsets[0] != 0)
-    {
-      rebased.resize((size_t)nseq + 1);
-      for (long long i = 0; i <= nseq; i++) rebased[(size_t)i] = offsets[i] - offsets[0];
-      src = rebased.data();
-    }
     SWB_CUDA(cudaEventRecord(db->ev_open[0], db->copy_stream));
-    SWB_CUDA(cudaMemcpyAsync(db->offsets.p, src, ((size_t)nseq + 1) * sizeof(long long),
+    SWB_CUDA(cudaMemcpyAsync(db->offsets.p, offsets, ((size_t)nseq + 1) * sizeof(long long),
                              cudaMemcpyHostToDevice, db->copy_stream));
-    if (!rebased.empty()) SWB_CUDA(cudaStreamSynchronize(db->copy_stream));
+    // host-side coordinates of the bytes that are copied: residue offsets, or .nsq record offsets
+    const long long *coord = offsets;
+    unsigned char *dst_base = db->residues.p;
+    if (S.nsq)
+    {
+      coord = S.pk_start.data();
+      SWB_TRY(db->packed.reserve((size_t)coord[nseq] + 16));
+      SWB_TRY(db->pk_start.reserve((size_t)nseq + 1));
+      SWB_TRY(db->pk_len.reserve((size_t)std::max<long long>(nseq, 1)));
+      SWB_CUDA(cudaMemcpyAsync(db->pk_start.p, coord, ((size_t)nseq + 1) * sizeof(long long),
+                               cudaMemcpyHostToDevice, db->copy_stream));
+      SWB_CUDA(cudaMemcpyAsync(db->pk_len.p, S.pk_len.data(), (size_t)nseq * sizeof(u32),
+                               cudaMemcpyHostToDevice, db->copy_stream));
+      dst_base = db->packed.p;
+    }
+    // pageable vectors owned by the caller's frame must be consumed before it returns
+    if (!S.own_offsets.empty() || S.nsq) SWB_CUDA(cudaStreamSynchronize(db->copy_stream));
+    size_t ext = 0;
     for (size_t c = 0; c + 1 < cut.size(); c++)
     {
       Layout *L = new (std::nothrow) Layout;
       if (!L) return SWB_ERR_NOMEM;
       db->chunks.push_back(L);
       const long long lo = cut[c], hi = cut[c + 1];
-      const long long b0 = offsets[lo] - offsets[0], b1 = offsets[hi] - offsets[0];
-      if (b1 > b0)
-        SWB_CUDA(cudaMemcpyAsync(db->residues.p + b0, residues + offsets[lo], (size_t)(b1 - b0),
-                                 cudaMemcpyHostToDevice, db->copy_stream));
+      while (ext < S.extents.size() && S.extents[ext].s1 <= lo) ext++;
+      for (size_t x = ext; x < S.extents.size() && S.extents[x].s0 < hi; x++)
+      {
+        const Extent &E = S.extents[x];
+        const long long a = std::max(lo, E.s0), b = std::min(hi, E.s1);
+        const long long bytes = coord[b] - coord[a];
+        if (bytes > 0)
+          SWB_CUDA(cudaMemcpyAsync(dst_base + coord[a], E.src + (coord[a] - coord[E.s0]), (size_t)bytes,
+                                   cudaMemcpyHostToDevice, db->copy_stream));
+      }
       SWB_CUDA(cudaEventCreateWithFlags(&L->ev_ready, cudaEventDisableTiming));
       cudaEvent_t up;
       SWB_CUDA(cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
@@ -826,8 +855,24 @@ static int open_impl(int device, const uint8_t *residues, const int64_t *offsets
       SWB_CUDA(cudaStreamWaitEvent(db->layout_stream, up, 0));
       SWB_CUDA(cudaEventDestroy(up));             // released once the wait has consumed it
       if (c == 0) SWB_CUDA(cudaEventRecord(db->ev_open[1], db->layout_stream));
-      SWB_TRY(build_layout(db, *L, nullptr, lo, hi - lo, b1 - b0, db->layout_stream));
+      if (S.nsq && hi > lo)
+      {
+        const long long warps = hi - lo;
+        swb_nt_decode_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, db->layout_stream>>>(
+            db->packed.p, db->pk_start.p, db->pk_len.p, db->offsets.p, db->residues.p, lo, hi - lo);
+        SWB_CUDA(cudaGetLastError());
+      }
+      SWB_TRY(build_layout(db, *L, nullptr, lo, hi - lo, offsets[hi] - offsets[lo], db->layout_stream));
       SWB_CUDA(cudaEventRecord(L->ev_ready, db->layout_stream));
+    }
+    // "uploaded" = the residue buffer is complete (for nsq: decoded), which the wide kernel needs
+    if (S.nsq)
+    {
+      cudaEvent_t done;
+      SWB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+      SWB_CUDA(cudaEventRecord(done, db->layout_stream));
+      SWB_CUDA(cudaStreamWaitEvent(db->copy_stream, done, 0));
+      SWB_CUDA(cudaEventDestroy(done));
     }
     SWB_CUDA(cudaEventRecord(db->ev_uploaded, db->copy_stream));
     SWB_CUDA(cudaEventRecord(db->ev_open[2], db->layout_stream));
@@ -845,16 +890,105 @@ static int open_impl(int device, const uint8_t *residues, const int64_t *offsets
   return SWB_OK;
 }
 
+// raw symbol bytes + offsets, as swb_db_open documents
+static int open_raw(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
+                    int trailing, void *stream, swb_db **out, bool wait)
+{
+  if (!out) return SWB_ERR_ARG;
+  *out = nullptr;
+  if (nseq < 0 || !offsets || trailing < 0 || trailing > 1 || nseq > 0x7ffffff0LL) return SWB_ERR_ARG;
+  const long long span = offsets[nseq] - offsets[0];
+  if (span < 0 || (span > 0 && !residues)) return SWB_ERR_ARG;
+  OpenSrc S;
+  S.nseq = nseq;
+  S.trailing = trailing;
+  for (long long i = 0; i < nseq; i++)
+  {
+    const long long len = offsets[i + 1] - offsets[i] - trailing;
+    if (len < 0 || len > 0x7fffffffLL) return SWB_ERR_ARG;
+    S.total += len;
+    S.longest = std::max(S.longest, len);
+  }
+  S.offsets = (const long long *)offsets;
+  if (offsets[0] != 0)                             // rebase so that residues[0] is the first byte uploaded
+  {
+    S.own_offsets.resize((size_t)nseq + 1);
+    for (long long i = 0; i <= nseq; i++) S.own_offsets[(size_t)i] = offsets[i] - offsets[0];
+    S.offsets = S.own_offsets.data();
+  }
+  if (nseq > 0) S.extents.push_back(Extent{0, nseq, residues + offsets[0]});
+  return open_impl(device, S, stream, out, wait);
+}
+
 int swb_db_open(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
                 int trailing, void *stream, swb_db **out)
 {
-  return open_impl(device, residues, offsets, nseq, trailing, stream, out, true);
+  return open_raw(device, residues, offsets, nseq, trailing, stream, out, true);
 }
 
 int swb_db_open_async(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
                       int trailing, void *stream, swb_db **out)
 {
-  return open_impl(device, residues, offsets, nseq, trailing, stream, out, false);
+  return open_raw(device, residues, offsets, nseq, trailing, stream, out, false);
+}
+
+// Upload subjects [first, first + count) of a BLAST database (all of it with count < 0): protein
+// volumes are copied as they lie in the .psq (NUL separated -> trailing = 1); nucleotide volumes are
+// copied packed (4 bases per byte + ambiguity tables) and unpacked on the device to the 4-bit codes
+// db_getsequence produces (database.cc:1257-1323).
+int swb_db_open_blast(int device, const swb_blastdb *b, int64_t first, int64_t count, int async,
+                      void *stream, swb_db **out)
+{
+  if (!out) return SWB_ERR_ARG;
+  *out = nullptr;
+  if (!b || first < 0 || first > b->nseq) return SWB_ERR_ARG;
+  if (count < 0 || first + count > b->nseq) count = b->nseq - first;
+  if (count > 0x7ffffff0LL) return SWB_ERR_ARG;
+  OpenSrc S;
+  S.nseq = count;
+  S.nsq = b->nucleotide;
+  S.trailing = b->nucleotide ? 0 : 1;
+  S.own_offsets.resize((size_t)count + 1);
+  if (S.nsq)
+  {
+    S.pk_start.resize((size_t)count + 1);
+    S.pk_len.resize((size_t)std::max<int64_t>(count, 1));
+  }
+  long long k = 0, off = 0, pk = 0;
+  for (const SwbVolume &v : b->vols)
+  {
+    const long long a = std::max<long long>(first, v.first) - v.first;
+    const long long e = std::min<long long>(first + count, v.first + v.nseq) - v.first;
+    if (e <= a) continue;
+    S.extents.push_back(Extent{k, k + (e - a), v.seq + v.seq_off(a)});
+    for (long long s = a; s < e; s++, k++)
+    {
+      const long long o1 = v.seq_off(s), o2 = v.seq_off(s + 1);
+      long long len;
+      if (S.nsq)
+      {
+        len = swb_nt_length(v, s);
+        S.pk_start[(size_t)k] = pk;
+        S.pk_len[(size_t)k] = (u32)(v.amb_off(s) - o1);
+        pk += o2 - o1;
+        S.own_offsets[(size_t)k] = off;
+        off += len;
+      }
+      else
+      {
+        len = o2 - o1 - 1;
+        if (len < 0) return SWB_ERR_ARG;
+        S.own_offsets[(size_t)k] = off;
+        off += o2 - o1;
+      }
+      S.total += len;
+      S.longest = std::max(S.longest, len);
+    }
+  }
+  S.own_offsets[(size_t)count] = off;
+  if (S.nsq) S.pk_start[(size_t)count] = pk;
+  S.offsets = S.own_offsets.data();
+  return open_impl(device, S, stream, out, async == 0);
 }
 
 int swb_db_wait(swb_db *db)
@@ -884,6 +1018,7 @@ int swb_db_close(swb_db *db)
   if (db->layout_stream) cudaStreamSynchronize(db->layout_stream);
   if (db->stream) cudaStreamSynchronize(db->stream);
   db->residues.release(); db->offsets.release(); db->tmp.release();
+  db->packed.release(); db->pk_start.release(); db->pk_len.release();
   for (Layout *L : db->chunks) { L->release(); delete L; }
   db->chunks.clear();
   db->m16.release(); db->qrow_off.release(); db->matrix.release(); db->query.release();

@@ -1,0 +1,140 @@
+"""TEST INFRASTRUCTURE: writes BLAST version-4 databases (the format the reference reads,
+database.cc:515-608, :1237-1401; asnparse.cc for the .phr deflines) so that the unmodified
+reference CLI (oracle/_ref/swipe) and our reader/ingest see the same bytes.  makeblastdb is not
+available offline; format facts are the ones listed at the end of SURVEY.md section 8."""
+import struct
+
+import numpy as np
+
+
+def _defline(seq_id, title):
+    """Minimal Blast-def-line-set, BER with indefinite lengths: parses as 'lcl|id title'."""
+    t = title.encode()
+    i = seq_id.encode()
+    assert len(t) < 128 and len(i) < 128
+    return (bytes([0x30, 0x80, 0x30, 0x80, 0xA0, 0x80, 0x1A, len(t)]) + t + bytes([0, 0]) +
+            bytes([0xA1, 0x80, 0x30, 0x80, 0xA0, 0x80, 0xA1, 0x80, 0x1A, len(i)]) + i +
+            bytes(12))
+
+
+def _index(path, protein, title, date, nseq, residues, longest, tables):
+    t = title.encode()
+    d = date.encode()
+    buf = struct.pack(">II", 4, 1 if protein else 0)
+    buf += struct.pack(">I", len(t)) + t + struct.pack(">I", len(d)) + d
+    buf += bytes(-len(buf) % 4)                      # database.cc:587-592
+    buf += struct.pack(">I", nseq) + struct.pack("<Q", residues) + struct.pack(">I", longest)
+    for tab in tables:
+        buf += np.asarray(tab, dtype=">u4").tobytes()
+    with open(path, "wb") as f:
+        f.write(buf)
+
+
+def write_protein(basename, subjects, title="synthetic protein db", date="Oct 17, 2026  5:00 AM",
+                  ids=None):
+    """subjects: uint8 arrays of NCBIstdaa codes 1..27.  Writes basename.pin/.psq/.phr."""
+    n = len(subjects)
+    ids = ids or ["s%d" % i for i in range(n)]
+    hdr, hoff = b"", [0]
+    for i in range(n):
+        hdr += _defline(ids[i], "subject %d" % i)
+        hoff.append(len(hdr))
+    sq = bytearray(b"\0")
+    soff = [1]
+    for s in subjects:
+        sq += np.asarray(s, dtype=np.uint8).tobytes() + b"\0"
+        soff.append(len(sq))
+    lens = [len(s) for s in subjects]
+    _index(basename + ".pin", True, title, date, n, int(sum(lens)), max(lens + [0]), [hoff, soff])
+    open(basename + ".psq", "wb").write(bytes(sq))
+    open(basename + ".phr", "wb").write(hdr)
+    return np.asarray(soff, dtype=np.int64)
+
+
+_TWOBIT = np.zeros(16, dtype=np.uint8)
+_TWOBIT[[1, 2, 4, 8]] = [0, 1, 2, 3]
+
+
+def pack_nt(codes, big_table=False):
+    """4-bit codes -> the .nsq record: 4 bases per byte MSB first, the last byte carries the
+    remaining len%4 bases and their count in its low two bits (database.cc:1260-1261), then the
+    ambiguity table (database.cc:1288-1322)."""
+    c = np.asarray(codes, dtype=np.uint8)
+    L = c.size
+    two = _TWOBIT[c & 15]
+    nfull = L // 4
+    out = bytearray()
+    if nfull:
+        q = two[:4 * nfull].reshape(-1, 4)
+        out += ((q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]).astype(np.uint8).tobytes()
+    last = 0
+    for k in range(L % 4):
+        last |= int(two[4 * nfull + k]) << (6 - 2 * k)
+    out.append(last | (L % 4))
+    amb = ~np.isin(c, [1, 2, 4, 8])
+    entries = []
+    i = 0
+    maxrun = 4096 if big_table else 16
+    while i < L:
+        if amb[i]:
+            j = i
+            while j < L and amb[j] and c[j] == c[i] and j - i < maxrun:
+                j += 1
+            entries.append((int(c[i]), j - i, i))
+            i = j
+        else:
+            i += 1
+    tail = b""
+    if entries:
+        if big_table:
+            tail = struct.pack(">I", 0x80000000 | (2 * len(entries)))
+            for code, run, off in entries:
+                tail += struct.pack(">Q", (code << 60) | ((run - 1) << 48) | off)
+        else:
+            tail = struct.pack(">I", len(entries))
+            for code, run, off in entries:
+                assert off < (1 << 24)
+                tail += struct.pack(">I", (code << 28) | ((run - 1) << 24) | off)
+    return bytes(out), tail
+
+
+def write_nucleotide(basename, subjects, title="synthetic nt db", date="Oct 17, 2026  5:00 AM",
+                     ids=None, big_table=False):
+    """subjects: uint8 arrays of 4-bit nt codes (A=1 C=2 G=4 T=8, others ambiguity).
+    Writes basename.nin/.nsq/.nhr; returns (seq_offsets[n+1], amb_offsets[n+1])."""
+    n = len(subjects)
+    ids = ids or ["s%d" % i for i in range(n)]
+    hdr, hoff = b"", [0]
+    for i in range(n):
+        hdr += _defline(ids[i], "subject %d" % i)
+        hoff.append(len(hdr))
+    sq = bytearray(b"\0")
+    soff, aoff = [], []
+    for s in subjects:
+        soff.append(len(sq))
+        packed, tail = pack_nt(s, big_table)
+        sq += packed
+        aoff.append(len(sq))
+        sq += tail
+    soff.append(len(sq))
+    aoff.append(len(sq))
+    lens = [len(s) for s in subjects]
+    _index(basename + ".nin", False, title, date, n, int(sum(lens)), max(lens + [0]),
+           [hoff, soff, aoff])
+    open(basename + ".nsq", "wb").write(bytes(sq))
+    open(basename + ".nhr", "wb").write(hdr)
+    return np.asarray(soff, dtype=np.int64), np.asarray(aoff, dtype=np.int64)
+
+
+AA = "-ABCDEFGHIKLMNPQRSTVWXYZU*OJ"
+NT = {1: "A", 2: "C", 4: "G", 8: "T", 15: "N", 5: "R", 10: "Y", 3: "M", 12: "K", 6: "S", 9: "W",
+      14: "B", 13: "D", 11: "H", 7: "V"}
+
+
+def write_fasta(path, codes, protein=True, name="query"):
+    c = np.asarray(codes, dtype=np.uint8)
+    text = "".join(AA[x] for x in c) if protein else "".join(NT[int(x)] for x in c)
+    with open(path, "w") as f:
+        f.write(">%s\n" % name)
+        for i in range(0, len(text), 60):
+            f.write(text[i:i + 60] + "\n")

@@ -46,3 +46,41 @@ def asym_matrix(seed=3):
     for a in range(1, 28):
         m[a, a] = int(rng.integers(3, 13))
     return m.reshape(-1)
+
+
+def blast_protein_subjects(query, seed=11):
+    """Subjects of the BLAST-file fixtures (two volumes' worth): edge cases + planted copies.
+    No zero-length subjects (makeblastdb never writes them)."""
+    rng = np.random.default_rng(seed)
+    res, off = edge_db(query, seed=seed)
+    subs = [res[off[i]:off[i + 1]] for i in range(off.size - 1)]
+    subs = [s if s.size else synth.random_protein(rng, 2) for s in subs]
+    pr, po = synth.protein_db(150, query=query, seed=seed + 1, plant_every=9, max_len=700)
+    subs += [pr[po[i]:po[i + 1]] for i in range(150)]
+    return subs
+
+
+def blast_nt_subjects(query, seed=12):
+    """Nucleotide subjects with every feature the .nsq format has: lengths of every residue class
+    mod 4, N runs longer than one ambiguity entry, single IUPAC codes, planted forward and
+    reverse-complement copies of query windows."""
+    rng = np.random.default_rng(seed)
+    qlen = len(query)
+    subs = []
+    for i in range(120):
+        L = int(rng.integers(1, 500)) if i >= 8 else i + 1
+        s = (1 << rng.integers(0, 4, size=L)).astype(np.uint8)
+        if i % 3 == 0 and L > 50:
+            w = min(L, 150)
+            st = int(rng.integers(0, qlen - w))
+            p = np.asarray(query[st:st + w]).copy()
+            if i % 2 == 0:
+                p = synth.revcomp_nt(p)
+            s[:w] = p
+        if i % 4 == 0 and L > 40:
+            a = int(rng.integers(0, L - 35))
+            s[a:a + int(rng.integers(1, 35))] = 15
+        if i % 7 == 0 and L > 10:
+            s[int(rng.integers(0, L))] = int(rng.choice([5, 10, 3, 12, 6, 9, 14, 13, 11, 7]))
+        subs.append(s)
+    return subs
