@@ -70,6 +70,22 @@ __device__ __forceinline__ u32 swb_hadd2(u32 a, u32 b)
   return r;
 }
 
+// relu(a + b) per fp16 lane: fma.rn.relu(a, 1.0, b).  Exact on the integer bit patterns like swb_hadd2.
+__device__ __forceinline__ u32 swb_hadd2_relu(u32 a, u32 b)
+{
+  u32 r;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3c003c00u), "r"(b));
+  return r;
+}
+// fp16x2 maximum: on bit patterns of non-negative integers (and sign-magnitude negatives) this is
+// the integer maximum; a 2-input op that issues at twice the rate of the 3-input DPX forms.
+__device__ __forceinline__ u32 swb_hmax2(u32 a, u32 b)
+{
+  u32 r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
 // Shared-memory access by 32-bit shared-window address (no generic-pointer arithmetic, no
 // alignment masks in the instruction stream).  The "memory" clobber keeps them ordered against
 // __syncthreads at the compiler level; ptxas schedules them like any other LDS/STS.

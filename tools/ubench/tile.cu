@@ -27,6 +27,42 @@ __device__ __forceinline__ void cell(u32 hd, u32 s, u32 &e, u32 &f, u32 &h, u32 
     e = __viaddmax_s16x2_relu(e, 0xffffffffu, hq);
     f = __viaddmax_s16x2_relu(f, 0xffffffffu, hq);
   }
+  if (V == 7)
+  { // F through the FMA pipe + a 2-input fp16 max; H - q with relu so that E, F stay >= 0
+    u32 a = swb_hadd2(hd, s);
+    h = __vimax3_s16x2_relu(a, e, f);
+    smax = __vmaxs2(smax, h);
+    u32 hq = swb_hadd2_relu(h, negq);
+    e = __viaddmax_s16x2_relu(e, negr, hq);
+    f = swb_hmax2(swb_hadd2(f, 0x80018001u), hq);
+  }
+  if (V == 8)
+  { // E and F both through FMA pipe + fp16 max
+    u32 a = swb_hadd2(hd, s);
+    h = __vimax3_s16x2_relu(a, e, f);
+    smax = __vmaxs2(smax, h);
+    u32 hq = swb_hadd2_relu(h, negq);
+    e = swb_hmax2(swb_hadd2(e, 0x80018001u), hq);
+    f = swb_hmax2(swb_hadd2(f, 0x80018001u), hq);
+  }
+  if (V == 9)
+  { // as 7, running maximum with the 2-input fp16 max
+    u32 a = swb_hadd2(hd, s);
+    h = __vimax3_s16x2_relu(a, e, f);
+    smax = swb_hmax2(smax, h);
+    u32 hq = swb_hadd2_relu(h, negq);
+    e = __viaddmax_s16x2_relu(e, negr, hq);
+    f = swb_hmax2(swb_hadd2(f, 0x80018001u), hq);
+  }
+  if (V == 10)
+  { // everything 2-input: h by two fp16 max (E, F >= 0 make the relu implicit)
+    u32 a = swb_hadd2(hd, s);
+    h = swb_hmax2(swb_hmax2(a, e), f);
+    smax = swb_hmax2(smax, h);
+    u32 hq = swb_hadd2_relu(h, negq);
+    e = swb_hmax2(swb_hadd2(e, 0x80018001u), hq);
+    f = swb_hmax2(swb_hadd2(f, 0x80018001u), hq);
+  }
   if (V == 4) swb_cell<SWB_MODE_INT16>(hd, s, e, f, h, smax, negq, negr);
   if (V == 5)
   { // E' = E + q formulation: no H - q add; a on the FMA pipe
@@ -86,7 +122,8 @@ __global__ void __launch_bounds__(128, 4) tile(u32 *out, const u32 *in, int step
 }
 
 static const char *names[] = {"hybrid cell as in the kernel", "hybrid, no running max", "hybrid, immediate penalties",
-                              "hybrid, scores from registers (no LDS)", "int16 cell", "E+q formulation", "hybrid + __syncthreads per step"};
+                              "hybrid, scores from registers (no LDS)", "int16 cell", "E+q formulation", "hybrid + __syncthreads per step",
+                              "F via hadd2+hmax2 (ALU 6 / FMA 6)", "E and F via hadd2+hmax2 (ALU 5 / FMA 8)", "as 7, smax by hmax2", "all 2-input fp16 max"};
 
 template <int V, int R> void run(u32 *dout, u32 *din, long long *dcyc, int nsm)
 {
@@ -121,6 +158,7 @@ int main()
   CK(cudaMemcpy(din, hin, sizeof hin, cudaMemcpyHostToDevice));
   run<0, 24>(dout, din, dcyc, nsm); run<1, 24>(dout, din, dcyc, nsm); run<2, 24>(dout, din, dcyc, nsm);
   run<3, 24>(dout, din, dcyc, nsm); run<4, 24>(dout, din, dcyc, nsm); run<5, 24>(dout, din, dcyc, nsm);
+  run<7, 24>(dout, din, dcyc, nsm); run<8, 24>(dout, din, dcyc, nsm); run<9, 24>(dout, din, dcyc, nsm); run<10, 24>(dout, din, dcyc, nsm);
   run<6, 24>(dout, din, dcyc, nsm); run<0, 12>(dout, din, dcyc, nsm); run<0, 8>(dout, din, dcyc, nsm); run<0, 16>(dout, din, dcyc, nsm); run<0, 20>(dout, din, dcyc, nsm); run<3, 12>(dout, din, dcyc, nsm);
   return 0;
 }
