@@ -184,6 +184,26 @@ int swb_search_end(swb_db *db, const uint8_t *query, int64_t qlen, const swb_sco
                    const int64_t *seqnos, int64_t n, int64_t *scores, int64_t *bestpos,
                    int64_t *bestq);
 
+/* ---- alignment of a hit (host) -------------------------------------------------------------
+ * swb_align: the reference's align() (align.cc:469-519) as hits_align calls it for the best -b hits
+ * (hits.cc:587-623).  Host code: a reverse pass from the end cell finds the start, then a
+ * linear-space divide-and-conquer recovers the path.  Ties are broken as the reference breaks
+ * them, so the same alignment is reported.
+ *   matrix, query, subject : as for the scan ([(subject_symbol << 5) + query_symbol])
+ *   gap_open, gap_extend   : -G / -E as given on the command line (NOT open+extend)
+ *   *score, *q_end, *d_end : in/out.  *score != 0 on entry = the end cell is already known (the
+ *                            hint from swb_search_end / search16s, hits.cc:589-600); 0 = find it
+ *                            with a forward pass (first strict maximum in query-major order)
+ *   q_start, d_start       : out, first aligned query / subject position (0-based)
+ *   ops                    : out, NUL-terminated run-length string "M<n>I<n>D<n>..." (M aligned
+ *                            pair, I subject symbols against a gap, D query symbols against a gap);
+ *                            *ops_len receives its length, SWB_ERR_RANGE if ops_cap is too small
+ */
+int swb_align(const uint8_t *query, int64_t qlen, const uint8_t *subject, int64_t dlen,
+              const int64_t *matrix, int64_t gap_open, int64_t gap_extend, int64_t *q_start,
+              int64_t *d_start, int64_t *q_end, int64_t *d_end, int64_t *score, char *ops,
+              int64_t ops_cap, int64_t *ops_len);
+
 /* ---- the sink ----------------------------------------------------------------------------
  * swb_topk_merge: the insertion rule of hits_enter (hits.cc:163-222) applied to the scores of
  * one or more shards: reject score < min_score or > upper_score, order by score descending then

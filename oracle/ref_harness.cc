@@ -262,4 +262,23 @@ void ref_search16s(const unsigned char *residues, const int64_t *offsets, long n
   free(dprofile); free(hearray); free(qtable);
 }
 
+// The reference's aligner (align.cc:469-519) as hits_align calls it (hits.cc:587-623): in/out
+// hints (*score != 0: alignment end already known), out: begin/end coordinates and the run-length
+// op string.  Uses the matrix set by ref_matrix_init.  Returns the op string length.
+long ref_align(const unsigned char *q, long qlen, const unsigned char *d, long dlen,
+               long gapopen, long gapextend, int64_t *coords /* qs, ds, qe, de */,
+               int64_t *score, char *ops, long ops_cap)
+{
+  long qs = 0, ds = 0, qe = coords[2], de = coords[3], s = *score;
+  char *alignment = NULL;
+  align((char *)q, (char *)d, qlen, dlen, score_matrix_63, gapopen, gapextend, &qs, &ds, &qe, &de,
+        &alignment, &s);
+  coords[0] = qs; coords[1] = ds; coords[2] = qe; coords[3] = de;
+  *score = s;
+  long n = (long)strlen(alignment);
+  if (n < ops_cap) memcpy(ops, alignment, n + 1);
+  free(alignment);
+  return n;
+}
+
 }  // extern "C"

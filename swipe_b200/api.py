@@ -18,7 +18,7 @@ EXPORTS = ["swb_abi_version", "swb_strerror", "swb_last_cuda_error", "swb_device
            "swb_db_open_ms", "swb_set_shape", "swb_db_open_async", "swb_db_wait", "swb_trim",
            "swb_blastdb_open", "swb_blastdb_close", "swb_blastdb_error", "swb_blastdb_info",
            "swb_blastdb_title", "swb_blastdb_date", "swb_blastdb_seqlen", "swb_blastdb_sequence",
-           "swb_blastdb_header", "swb_blastdb_included", "swb_db_open_blast"]
+           "swb_blastdb_header", "swb_blastdb_included", "swb_db_open_blast", "swb_align"]
 
 
 class SwbError(RuntimeError):
@@ -102,6 +102,9 @@ def load_library():
     lib.swb_blastdb_included.argtypes = [C.c_void_p, C.c_int64]
     lib.swb_db_open_blast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
                                       C.POINTER(C.c_void_p)]
+    lib.swb_align.restype = C.c_int
+    lib.swb_align.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                              C.c_int64, p64, p64, p64, p64, p64, C.c_char_p, C.c_int64, p64]
     for name in ("swb_blastdb_open", "swb_blastdb_close", "swb_blastdb_info", "swb_blastdb_sequence",
                  "swb_blastdb_header", "swb_blastdb_included", "swb_db_open_blast"):
         getattr(lib, name).restype = C.c_int
@@ -334,6 +337,24 @@ class Database:
                                         coded.ctypes.data, coded.size, scores.ctypes.data,
                                         bestpos.ctypes.data, bestq.ctypes.data))
         return scores, bestpos, bestq
+
+
+def align(query, subject, scoring, hint=None):
+    """swb_align: (score, q_start, d_start, q_end, d_end, ops).  hint = (score, q_end, d_end) from
+    search_end (hits.cc:589-600) or None to let the aligner find the end cell itself."""
+    lib = load_library()
+    q, d = _u8(query), _u8(subject)
+    vals = [C.c_int64(0) for _ in range(5)]                  # q_start d_start q_end d_end score
+    if hint is not None:
+        vals[4].value, vals[2].value, vals[3].value = int(hint[0]), int(hint[1]), int(hint[2])
+    cap = 16 * (q.size + d.size) + 64
+    buf = C.create_string_buffer(cap)
+    n = C.c_int64()
+    _check(lib.swb_align(q.ctypes.data, q.size, d.ctypes.data, d.size, scoring.matrix.ctypes.data,
+                         scoring.gap_open, scoring.gap_extend, C.byref(vals[0]), C.byref(vals[1]),
+                         C.byref(vals[2]), C.byref(vals[3]), C.byref(vals[4]), buf, cap, C.byref(n)))
+    return (vals[4].value, vals[0].value, vals[1].value, vals[2].value, vals[3].value,
+            buf.value.decode())
 
 
 def topk_merge(score_arrays, seqno_bases, keep, min_score=0, upper_score=2 ** 62):

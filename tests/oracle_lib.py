@@ -122,7 +122,26 @@ class Ref:
         lib.ref_scan.argtypes = [_p, _p, _l, _p, _l, _l, _l, C.c_int, _l, C.c_int, _p, _p, _p]
         lib.ref_search16.argtypes = [_p, _p, _l, _p, _l, _l, _l, _p, _p]
         lib.ref_search16s.argtypes = [_p, _p, _l, _p, _l, _l, _l, _p, _p, _p]
+        if hasattr(lib, "ref_align"):
+            lib.ref_align.restype = _l
+            lib.ref_align.argtypes = [_p, _l, _p, _l, _l, _l, _p, _p, C.c_char_p, _l]
         self.lib = lib
+
+    def align(self, q, d, gap_open, gap_extend, hint=None):
+        """The reference's align() (align.cc:469-519) with the matrix of the last matrix_init:
+        (score, q_start, d_start, q_end, d_end, ops)."""
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        d = np.ascontiguousarray(d, dtype=np.uint8)
+        coords = np.zeros(4, dtype=np.int64)
+        score = C.c_int64(0)
+        if hint is not None:
+            score.value, coords[2], coords[3] = int(hint[0]), int(hint[1]), int(hint[2])
+        cap = 16 * (q.size + d.size) + 64
+        buf = C.create_string_buffer(cap)
+        self.lib.ref_align(q.ctypes.data, q.size, d.ctypes.data, d.size, gap_open, gap_extend,
+                           coords.ctypes.data, C.byref(score), buf, cap)
+        return (int(score.value), int(coords[0]), int(coords[1]), int(coords[2]), int(coords[3]),
+                buf.value.decode())
 
     def matrix_init(self, name="BLOSUM62", symtype=1, match=1, mismatch=-3):
         self.lib.ref_matrix_init(name.encode(), symtype, match, mismatch)

@@ -68,3 +68,20 @@ def test_asymmetric_golden():
     with Database(g["residues"], g["offsets"]) as db:
         got = db.search(g["query"], Scoring(g["matrix"].astype(np.int64), 7, 2))
     assert np.array_equal(got, g["scores"])
+
+
+def test_alignment_phase_golden():
+    """align_chunk (swipe.cc:339-414): the end cells from the GPU (search16s's contract) are the
+    hints of the host traceback; the alignments must be the ones the reference's align() gave."""
+    import json
+    from swipe_b200 import align
+    recs = [r for r in json.load(open(os.path.join(G, "align.json")))["protein"] if "hint" in r]
+    p = load("protein.npz")
+    sc = Scoring(scoring.blosum62(), 11, 1)
+    subjects = np.array([r["subject"] for r in recs])
+    with Database(p["residues"], p["offsets"]) as db:
+        s, bp, bq = db.search_end(p["query"], sc, subjects)
+    for k, r in enumerate(recs):
+        assert [int(s[k]), int(bq[k]), int(bp[k])] == r["hint"]
+        d = p["residues"][p["offsets"][r["subject"]]:p["offsets"][r["subject"] + 1]]
+        assert list(align(p["query"], d, sc, hint=(s[k], bq[k], bp[k]))) == r["hinted"]
