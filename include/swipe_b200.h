@@ -184,6 +184,55 @@ int swb_search_end(swb_db *db, const uint8_t *query, int64_t qlen, const swb_sco
                    const int64_t *seqnos, int64_t n, int64_t *scores, int64_t *bestpos,
                    int64_t *bestq);
 
+/* ---- scoring system and statistics (host) ---------------------------------------------------
+ * Substitution tables as score_matrix_init builds them (matrices.cc:520-591): 32 x 32,
+ * [(subject << 5) + query], -1 where undefined.
+ */
+int swb_matrix_builtin(const char *name, int64_t *matrix);        /* BLOSUM45/50/62/80/90, PAM30/70/250, identity_5_1 */
+int swb_matrix_parse(const char *text, int64_t *matrix);          /* matrix file text (matrices.cc:437-517) */
+int swb_matrix_read(const char *name_or_path, int64_t *matrix);   /* built-in name, else a file */
+int swb_matrix_nucleotide(int64_t match, int64_t mismatch, int64_t *matrix);   /* matrices.cc:533-538 */
+int swb_matrix_limits(const int64_t *matrix, int64_t *lo, int64_t *hi, int64_t *limit7, int64_t *limit16);
+
+/* Karlin-Altschul parameters (NCBI BLAST's tables; stats.cc:44-325): params = lambda, K, H, alpha,
+ * beta.  Return 1 when the scoring system is tabulated, 0 otherwise.                            */
+int swb_stats_params(const char *matrix, int64_t gap_open, int64_t gap_extend, double *params);
+int swb_stats_params_nt(int64_t match, int64_t mismatch, int64_t gap_open, int64_t gap_extend, double *params);
+int swb_stats_default_gaps(const char *matrix, int64_t *gap_open, int64_t *gap_extend);
+int64_t swb_stats_length_adjustment(double K, double alpha_d_lambda, double beta, int64_t qlen,
+                                    int64_t dblen, int64_t nseq);
+
+/* The search space and raw-score window hits_init derives (hits.cc:283-511). */
+typedef struct swb_stats
+{
+  int available;                 /* 0: no parameters for this scoring system, scores only          */
+  double lambda, K, H, alpha, beta, logK, Kmn;
+  int64_t length_adjustment, m, n;
+  int64_t score_threshold;       /* hits below are dropped: max(minscore, ceil(-ln(expect/Kmn)/lambda)) */
+  int64_t upper_threshold;       /* hits above are "obvious" and dropped (-u / -k)                  */
+} swb_stats;
+int swb_stats_init(int symtype, const char *matrix, int64_t match, int64_t mismatch, int64_t gap_open,
+                   int64_t gap_extend, int64_t qlen, int64_t symcount, int64_t seqcount,
+                   int64_t effdbsize, int64_t minscore, int64_t maxscore, double expect,
+                   double minexpect, swb_stats *out);
+double swb_stats_evalue(const swb_stats *st, int64_t score);     /* Kmn * exp(-lambda * score) */
+double swb_stats_bits(const swb_stats *st, int64_t score);       /* (lambda * score - ln K) / ln 2 */
+
+/* ---- query text, translation, deflines (host) ------------------------------------------------ */
+/* One FASTA record -> symbol codes (query.cc:244-355); returns the bytes of text consumed.       */
+int64_t swb_query_parse(const char *text, int64_t text_len, int nucleotide, uint8_t *seq,
+                        int64_t seq_cap, int64_t *seq_len, char *descr, int64_t descr_cap);
+int swb_revcomp(const uint8_t *seq, int64_t len, uint8_t *out);   /* 4-bit nt codes (query.cc:357-364) */
+/* 4096-entry codon table of NCBI genetic code 1..23 over 4-bit nucleotide codes (query.cc:366-436) */
+int swb_translate_table(int gencode, uint8_t *table);
+const char *swb_gencode_name(int gencode);
+int64_t swb_translate(const uint8_t *nt, int64_t len, int strand, int frame, const uint8_t *table,
+                      uint8_t *out);                               /* query.cc:450-506 */
+/* The deflines of a .phr/.nhr record as text, one per line (asnparse.cc:753-887); returns their
+ * count, *needed = bytes required (SWB_ERR_RANGE when cap is too small).                         */
+int64_t swb_defline_text(const uint8_t *data, int64_t len, int show_gis, int show_taxid, int64_t memb,
+                         char *buf, int64_t cap, int64_t *needed);
+
 /* ---- alignment of a hit (host) -------------------------------------------------------------
  * swb_align: the reference's align() (align.cc:469-519) as hits_align calls it for the best -b hits
  * (hits.cc:587-623).  Host code: a reverse pass from the end cell finds the start, then a
