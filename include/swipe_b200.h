@@ -158,6 +158,13 @@ int swb_blastdb_included(const swb_blastdb *b, int64_t seqno);
 int swb_db_open_blast(int device, const swb_blastdb *b, int64_t first, int64_t count, int async,
                       void *stream, swb_db **db);
 
+/* Same for a nucleotide database searched as six-frame translated protein (-p 3 / -p 4): sequence
+ * first + s becomes subjects 6 s + 3 strand + frame (search_chunk's order, swipe.cc:1377-1385),
+ * unpacked and translated on the device (db_translate, database.cc:1182-1218) with the codon table
+ * of swb_translate_table.                                                                        */
+int swb_db_open_blast_translated(int device, const swb_blastdb *b, int64_t first, int64_t count,
+                                 const uint8_t *codon_table, int async, void *stream, swb_db **db);
+
 /* ---- the hot path ------------------------------------------------------------------------
  * swb_search: what search_chunk's cascade (swipe.cc:1416-1594) yields for every subject of the
  * shard: scores[i] = exact affine-gap local alignment score of the query against subject i, in
@@ -179,6 +186,8 @@ int swb_search_list(swb_db *db, const uint8_t *query, int64_t qlen, const swb_sc
  * align_chunk swipe.cc:381-393): exact score plus the alignment end -- bestpos = first subject
  * column (0-based) in which the maximum is reached, bestq = smallest query row reaching it in
  * that column; both -1 when the score is 0.  Scores are exact (never saturated at 65535).
+ * A set strand bit (seqnos[k] & 4) scores the reverse complement of a nucleotide subject, which is
+ * how align_chunk asks for minus-strand hits (swipe.cc:355-361, database.cc:1327-1353).
  */
 int swb_search_end(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
                    const int64_t *seqnos, int64_t n, int64_t *scores, int64_t *bestpos,

@@ -48,6 +48,24 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+CLI = os.path.join(CSRC, "swipe-b200")
+
+
+def build_cli(force=False):
+    """The command-line front end (host C++ over the C ABI): swipe_b200/csrc/swipe-b200."""
+    src = os.path.join(CSRC, "swipe_main.cpp")
+    if not force and not _stale(CLI, ["swipe_main.cpp", LIB, os.path.join(ROOT, "include", "swipe_b200.h")]):
+        return CLI
+    cxx = shutil.which("g++")
+    if cxx is None:
+        if os.path.exists(CLI):
+            return CLI
+        raise RuntimeError("g++ not found and %s is not built" % CLI)
+    subprocess.run([cxx, "-O2", "-std=c++17", "-Wall", "-o", CLI, src, "-L" + CSRC, "-lswipe_b200",
+                    "-Wl,-rpath,$ORIGIN", "-lpthread"], check=True)
+    return CLI
+
+
 def build_oracle():
     """TEST INFRASTRUCTURE: the plain-C oracle and, where /root/reference exists, the unmodified
     reference kernels under oracle/_ref (see oracle/Makefile)."""
@@ -57,5 +75,6 @@ def build_oracle():
 if __name__ == "__main__":
     import sys
     build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_cli(force="--force" in sys.argv)
     build_oracle()
     print(LIB)

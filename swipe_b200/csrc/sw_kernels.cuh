@@ -422,6 +422,9 @@ __global__ void __launch_bounds__(128) swb_wide_kernel(const WideParams P)
   if (tid >= P.nsel) return;
   const long long item = P.sel ? P.sel[tid] : tid;
   const long long subj = P.list ? (P.list[item] >> 3) : item;
+  // strand bit of the coded subject number (swipe.cc:1373-1391): score against the reverse
+  // complement of a nucleotide subject, as db_getsequence serves it (database.cc:1327-1353)
+  const bool rc = P.list ? ((P.list[item] >> 2) & 1) != 0 : false;
   const long long o0 = P.offsets[subj];
   const long long dlen = P.offsets[subj + 1] - o0 - P.trailing;
   const unsigned char *d = P.residues + o0;
@@ -434,7 +437,9 @@ __global__ void __launch_bounds__(128) swb_wide_kernel(const WideParams P)
   long long bq = -1, bd = -1;
   for (long long j = 0; j < dlen; j++)
   {
-    const T *row = Msh + ((d[j] & 31) << 5);
+    unsigned sym = d[rc ? dlen - 1 - j : j] & 31;
+    if (rc) sym = ((sym & 1) << 3) | ((sym & 2) << 1) | ((sym & 4) >> 1) | ((sym & 8) >> 3);
+    const T *row = Msh + (sym << 5);
     T f = 0, h = 0;
     for (int i = 0; i < qlen; i++)
     {
@@ -519,6 +524,48 @@ __global__ void swb_nt_decode_kernel(const unsigned char *packed, const long lon
       const unsigned char code = (unsigned char)(e >> 28);
       const long long run = (long long)((e >> 24) & 0xf) + 1, off = (long long)(e & 0x00ffffffu);
       for (long long r = 0; r < run && off + r < len; r++) dst[off + r] = code;
+    }
+  }
+}
+
+// Six-frame translation of decoded nucleotide subjects (db_translate, database.cc:1182-1218, with
+// the table of query.cc:366-436): one warp per nucleotide sequence s writes the protein subjects
+// 6 s + 3 strand + frame.  Strand 1 reads the reverse complement from the far end.
+__global__ void swb_translate_kernel(const unsigned char *nt, const long long *nt_offsets,
+                                     const unsigned char *table, const long long *offsets,
+                                     unsigned char *residues, long long first, long long n)
+{
+  __shared__ unsigned char tab[4096];
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) tab[i] = table[i];
+  __syncthreads();
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const long long s = first + w;
+  const unsigned char *src = nt + nt_offsets[s];
+  const long long len = nt_offsets[s + 1] - nt_offsets[s];
+  for (int k = 0; k < 6; k++)
+  {
+    const int strand = k / 3, frame = k % 3;
+    const long long plen = len - frame >= 0 ? (len - frame) / 3 : 0;
+    unsigned char *dst = residues + offsets[6 * s + k];
+    for (long long p = lane; p < plen; p += 32)
+    {
+      u32 a, b, c;
+      if (!strand)
+      {
+        const long long pos = frame + 3 * p;
+        a = src[pos] & 15; b = src[pos + 1] & 15; c = src[pos + 2] & 15;
+      }
+      else
+      {
+        const long long pos = len - 1 - frame - 3 * p;
+        a = src[pos] & 15; b = src[pos - 1] & 15; c = src[pos - 2] & 15;
+        a = ((a & 1) << 3) | ((a & 2) << 1) | ((a & 4) >> 1) | ((a & 8) >> 3);
+        b = ((b & 1) << 3) | ((b & 2) << 1) | ((b & 4) >> 1) | ((b & 8) >> 3);
+        c = ((c & 1) << 3) | ((c & 2) << 1) | ((c & 4) >> 1) | ((c & 8) >> 3);
+      }
+      dst[p] = tab[(a << 8) | (b << 4) | c];
     }
   }
 }

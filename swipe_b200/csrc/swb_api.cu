@@ -184,6 +184,9 @@ struct swb_db
   DevBuf<unsigned char> packed;        // .nsq bytes as uploaded (nucleotide databases only)
   DevBuf<long long> pk_start;          // [nseq+1] start of every subject's record in packed
   DevBuf<u32> pk_len;                  // [nseq] bytes of packed bases in the record (rest: ambiguity table)
+  DevBuf<unsigned char> nt_residues;   // decoded nucleotides of a translated shard (source of the 6 frames)
+  DevBuf<long long> nt_offsets;        // [nsrc+1]
+  DevBuf<unsigned char> ttable;        // [4096] codon table
   std::vector<Layout *> chunks;   // the whole shard, cut into upload/layout/scan pipeline chunks
   Layout tmp;      // ad-hoc list layouts
   cudaStream_t copy_stream = nullptr, layout_stream = nullptr;
@@ -422,7 +425,9 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
   if (h_list)
     for (long long k = 0; k < n; k++)
     {
-      if ((h_list[k] & 7) != 0) return SWB_ERR_ARG;           // strand / frame must be 0
+      // frames never reach the kernels (translated subjects are separate entries of the shard);
+      // the strand bit is honoured by the end-cell search only
+      if ((h_list[k] & 3) != 0 || ((h_list[k] & 4) != 0 && !want_end)) return SWB_ERR_ARG;
       const long long s = h_list[k] >> 3;
       if (s < 0 || s >= db->nseq) return SWB_ERR_ARG;
     }
@@ -751,9 +756,14 @@ struct OpenSrc
   std::vector<long long> own_offsets;
   long long total = 0, longest = 0;
   bool nsq = false;
-  std::vector<long long> pk_start;        // [nseq+1] record offsets in the packed buffer (nsq)
-  std::vector<u32> pk_len;                // [nseq]
-  std::vector<Extent> extents;
+  std::vector<long long> pk_start;        // [nsrc+1] record offsets in the packed buffer (nsq)
+  std::vector<u32> pk_len;                // [nsrc]
+  std::vector<Extent> extents;            // in source sequences
+  // translated shards: every nucleotide source sequence s yields the six protein subjects
+  // 6 s + 3 strand + frame; offsets / nseq describe those, nt_offsets the decoded nucleotides
+  bool translate = false;
+  std::vector<long long> nt_offsets;      // [nsrc+1]
+  const uint8_t *ttable = nullptr;        // [4096]
 };
 
 static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wait)
@@ -785,15 +795,18 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
   long long chunk_bytes = 256LL << 20;
   if (const char *env = getenv("SWB_CHUNK_BYTES"))      // test hook: force many small chunks
     chunk_bytes = std::max<long long>(1, atoll(env));
-  std::vector<long long> cut;                       // chunk c covers subjects [cut[c], cut[c+1])
+  const int unit = S.translate ? 6 : 1;             // subjects per source sequence
+  const long long nsrc = nseq / unit;
+  const long long *cut_off = S.translate ? S.nt_offsets.data() : offsets;
+  std::vector<long long> cut;                       // chunk c covers source sequences [cut[c], cut[c+1])
   cut.push_back(0);
-  while (cut.back() < nseq)
+  while (cut.back() < nsrc)
   {
     const long long lo = cut.back();
-    const long long *e = std::upper_bound(offsets + lo + 1, offsets + nseq + 1, offsets[lo] + chunk_bytes);
-    long long hi = (long long)(e - offsets) - 1;     // last subject boundary within the byte budget
+    const long long *e = std::upper_bound(cut_off + lo + 1, cut_off + nsrc + 1, cut_off[lo] + chunk_bytes);
+    long long hi = (long long)(e - cut_off) - 1;     // last boundary within the byte budget
     if (hi <= lo) hi = lo + 1;
-    if (nseq - hi < (hi - lo) / 4) hi = nseq;        // do not leave a sliver behind
+    if (nsrc - hi < (hi - lo) / 4) hi = nsrc;        // do not leave a sliver behind
     cut.push_back(hi);
   }
 
@@ -820,14 +833,23 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
     if (S.nsq)
     {
       coord = S.pk_start.data();
-      SWB_TRY(db->packed.reserve((size_t)coord[nseq] + 16));
-      SWB_TRY(db->pk_start.reserve((size_t)nseq + 1));
-      SWB_TRY(db->pk_len.reserve((size_t)std::max<long long>(nseq, 1)));
-      SWB_CUDA(cudaMemcpyAsync(db->pk_start.p, coord, ((size_t)nseq + 1) * sizeof(long long),
+      SWB_TRY(db->packed.reserve((size_t)coord[nsrc] + 16));
+      SWB_TRY(db->pk_start.reserve((size_t)nsrc + 1));
+      SWB_TRY(db->pk_len.reserve((size_t)std::max<long long>(nsrc, 1)));
+      SWB_CUDA(cudaMemcpyAsync(db->pk_start.p, coord, ((size_t)nsrc + 1) * sizeof(long long),
                                cudaMemcpyHostToDevice, db->copy_stream));
-      SWB_CUDA(cudaMemcpyAsync(db->pk_len.p, S.pk_len.data(), (size_t)nseq * sizeof(u32),
+      SWB_CUDA(cudaMemcpyAsync(db->pk_len.p, S.pk_len.data(), (size_t)nsrc * sizeof(u32),
                                cudaMemcpyHostToDevice, db->copy_stream));
       dst_base = db->packed.p;
+    }
+    if (S.translate)
+    {
+      SWB_TRY(db->nt_residues.reserve((size_t)S.nt_offsets[(size_t)nsrc] + 16));
+      SWB_TRY(db->nt_offsets.reserve((size_t)nsrc + 1));
+      SWB_TRY(db->ttable.reserve(4096));
+      SWB_CUDA(cudaMemcpyAsync(db->nt_offsets.p, S.nt_offsets.data(), ((size_t)nsrc + 1) * sizeof(long long),
+                               cudaMemcpyHostToDevice, db->copy_stream));
+      SWB_CUDA(cudaMemcpyAsync(db->ttable.p, S.ttable, 4096, cudaMemcpyHostToDevice, db->copy_stream));
     }
     // pageable vectors owned by the caller's frame must be consumed before it returns
     if (!S.own_offsets.empty() || S.nsq) SWB_CUDA(cudaStreamSynchronize(db->copy_stream));
@@ -858,11 +880,20 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
       if (S.nsq && hi > lo)
       {
         const long long warps = hi - lo;
-        swb_nt_decode_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, db->layout_stream>>>(
-            db->packed.p, db->pk_start.p, db->pk_len.p, db->offsets.p, db->residues.p, lo, hi - lo);
+        const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+        swb_nt_decode_kernel<<<grid, 256, 0, db->layout_stream>>>(
+            db->packed.p, db->pk_start.p, db->pk_len.p, S.translate ? db->nt_offsets.p : db->offsets.p,
+            S.translate ? db->nt_residues.p : db->residues.p, lo, hi - lo);
         SWB_CUDA(cudaGetLastError());
+        if (S.translate)
+        {
+          swb_translate_kernel<<<grid, 256, 0, db->layout_stream>>>(
+              db->nt_residues.p, db->nt_offsets.p, db->ttable.p, db->offsets.p, db->residues.p, lo, hi - lo);
+          SWB_CUDA(cudaGetLastError());
+        }
       }
-      SWB_TRY(build_layout(db, *L, nullptr, lo, hi - lo, offsets[hi] - offsets[lo], db->layout_stream));
+      SWB_TRY(build_layout(db, *L, nullptr, lo * unit, (hi - lo) * unit,
+                           offsets[hi * unit] - offsets[lo * unit], db->layout_stream));
       SWB_CUDA(cudaEventRecord(L->ev_ready, db->layout_stream));
     }
     // "uploaded" = the residue buffer is complete (for nsq: decoded), which the wide kernel needs
@@ -991,6 +1022,61 @@ int swb_db_open_blast(int device, const swb_blastdb *b, int64_t first, int64_t c
   return open_impl(device, S, stream, out, async == 0);
 }
 
+// A nucleotide database as six-frame translated protein subjects (the reference's -p 3 / -p 4,
+// db_translate database.cc:1182-1218): sequence s of the shard becomes subjects 6 s + 3 strand +
+// frame (the order search_chunk lists them in, swipe.cc:1377-1385), translated ON THE DEVICE with
+// the 4096-entry codon table of swb_translate_table.
+int swb_db_open_blast_translated(int device, const swb_blastdb *b, int64_t first, int64_t count,
+                                 const uint8_t *codon_table, int async, void *stream, swb_db **out)
+{
+  if (!out) return SWB_ERR_ARG;
+  *out = nullptr;
+  if (!b || !b->nucleotide || !codon_table || first < 0 || first > b->nseq) return SWB_ERR_ARG;
+  if (count < 0 || first + count > b->nseq) count = b->nseq - first;
+  if (count > 0x7ffffff0LL / 6) return SWB_ERR_ARG;
+  OpenSrc S;
+  S.nseq = 6 * count;
+  S.nsq = true;
+  S.translate = true;
+  S.trailing = 0;
+  S.ttable = codon_table;
+  S.own_offsets.resize((size_t)(6 * count) + 1);
+  S.nt_offsets.resize((size_t)count + 1);
+  S.pk_start.resize((size_t)count + 1);
+  S.pk_len.resize((size_t)std::max<int64_t>(count, 1));
+  long long k = 0, off = 0, ntoff = 0, pk = 0;
+  for (const SwbVolume &v : b->vols)
+  {
+    const long long a = std::max<long long>(first, v.first) - v.first;
+    const long long e = std::min<long long>(first + count, v.first + v.nseq) - v.first;
+    if (e <= a) continue;
+    S.extents.push_back(Extent{k, k + (e - a), v.seq + v.seq_off(a)});
+    for (long long s = a; s < e; s++, k++)
+    {
+      const long long o1 = v.seq_off(s), o2 = v.seq_off(s + 1);
+      const long long len = swb_nt_length(v, s);
+      S.pk_start[(size_t)k] = pk;
+      S.pk_len[(size_t)k] = (u32)(v.amb_off(s) - o1);
+      pk += o2 - o1;
+      S.nt_offsets[(size_t)k] = ntoff;
+      ntoff += len;
+      for (int f = 0; f < 6; f++)
+      {
+        const long long plen = len - (f % 3) >= 0 ? (len - (f % 3)) / 3 : 0;
+        S.own_offsets[(size_t)(6 * k + f)] = off;
+        off += plen;
+        S.total += plen;
+        S.longest = std::max(S.longest, plen);
+      }
+    }
+  }
+  S.own_offsets[(size_t)(6 * count)] = off;
+  S.nt_offsets[(size_t)count] = ntoff;
+  S.pk_start[(size_t)count] = pk;
+  S.offsets = S.own_offsets.data();
+  return open_impl(device, S, stream, out, async == 0);
+}
+
 int swb_db_wait(swb_db *db)
 {
   if (!db) return SWB_ERR_ARG;
@@ -1019,6 +1105,7 @@ int swb_db_close(swb_db *db)
   if (db->stream) cudaStreamSynchronize(db->stream);
   db->residues.release(); db->offsets.release(); db->tmp.release();
   db->packed.release(); db->pk_start.release(); db->pk_len.release();
+  db->nt_residues.release(); db->nt_offsets.release(); db->ttable.release();
   for (Layout *L : db->chunks) { L->release(); delete L; }
   db->chunks.clear();
   db->m16.release(); db->qrow_off.release(); db->matrix.release(); db->query.release();

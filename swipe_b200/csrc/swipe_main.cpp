@@ -1,0 +1,972 @@
+// swipe_main.cpp -- command-line front end over the C ABI of include/swipe_b200.h: the reference's
+// options, run header, hit list, statistics and report formats (plain, XML, tab-separated) with the
+// database scan on one or more B200s.
+//
+// Takes over from the reference (torognes/swipe):
+//   args_init / args_show ................. swipe.cc:665-782, :827-1157
+//   work / main ........................... swipe.cc:2436-2611
+//   search_chunk's strand / frame loops ... swipe.cc:1365-1596 (the scoring itself: swb_search)
+//   hits_enter / hits_sort ................ hits.cc:78-222
+//   align_chunk / hits_align .............. swipe.cc:339-414, hits.cc:546-623 (swb_search_end + swb_align)
+//   hits_show_plain / _xml / _tsv ......... hits.cc:647-1176, :1660-1945
+//   show_deflines ......................... asnparse.cc:889-971
+// Not carried over: -x taxid lists, -N dump, -m 99, symtype 5, MPI.  `-a` (threads in the
+// reference) selects how many GPUs share the database, one host thread each.
+#include "../../include/swipe_b200.h"
+
+#include <getopt.h>
+#include <strings.h>
+#include <sys/times.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#define SWB_CLI_VERSION "0.1 (B200)"
+
+namespace
+{
+
+FILE *out = stdout;
+
+[[noreturn]] void fatal(const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vfprintf(stderr, fmt, ap);
+  va_end(ap);
+  fprintf(stderr, "\n");
+  exit(1);
+}
+
+void check(int rc, const char *what)
+{
+  if (rc == SWB_OK) return;
+  const char *detail = rc == SWB_ERR_IO ? swb_blastdb_error() : swb_last_cuda_error();
+  fatal("%s: %s%s%s", what, swb_strerror(rc), detail && *detail ? " - " : "", detail ? detail : "");
+}
+
+struct Options
+{
+  long gapopen = 0, gapextend = 0;
+  std::string matrixname, queryname = "-", databasename;
+  long minscore = 1, maxscore = LONG_MAX, maxmatches = 250, alignments = 100, threads = 1, view = 0;
+  long symtype = 1, show_gis = 0, show_taxid = 0;
+  double expect = 10.0, minexpect = 0.0;
+  long matchscore = 1, mismatchscore = -3, querystrands = 3, query_gencode = 1, db_gencode = 1;
+  long effdbsize = 0;
+  const char *outfile = nullptr;
+};
+
+const char SYM_AA[] = "-ABCDEFGHIKLMNPQRSTVWXYZU*OJ####";
+const char SYM_NT[] = "-acmgrsvtwyhkdbn################";
+
+void usage(const char *prog)
+{
+  fprintf(out, "Usage: %s [OPTIONS]\n", prog);
+  fprintf(out, "  -h, --help                 show help\n");
+  fprintf(out, "  -d, --db=FILE              sequence database base name (required)\n");
+  fprintf(out, "  -i, --query=FILE           query sequence filename (stdin)\n");
+  fprintf(out, "  -M, --matrix=NAME/FILE     score matrix name or filename (BLOSUM62)\n");
+  fprintf(out, "  -q, --penalty=NUM          penalty for nucleotide mismatch (-3)\n");
+  fprintf(out, "  -r, --reward=NUM           reward for nucleotide match (1)\n");
+  fprintf(out, "  -G, --gapopen=NUM          gap open penalty (11)\n");
+  fprintf(out, "  -E, --gapextend=NUM        gap extension penalty (1)\n");
+  fprintf(out, "  -v, --num_descriptions=NUM sequence descriptions to show (250)\n");
+  fprintf(out, "  -b, --num_alignments=NUM   sequence alignments to show (100)\n");
+  fprintf(out, "  -e, --evalue=REAL          maximum expect value of sequences to show (10.0)\n");
+  fprintf(out, "  -k, --minevalue=REAL       minimum expect value of sequences to show (0.0)\n");
+  fprintf(out, "  -c, --min_score=NUM        minimum score of sequences to show (1)\n");
+  fprintf(out, "  -u, --max_score=NUM        maximum score of sequences to show (inf.)\n");
+  fprintf(out, "  -a, --num_threads=NUM      number of GPUs to use, one host thread each (1)\n");
+  fprintf(out, "  -m, --outfmt=NUM           output format [0,7-9=plain,xml,tsv,tsv+] (0)\n");
+  fprintf(out, "  -I, --show_gis             show gi numbers in results (no)\n");
+  fprintf(out, "  -p, --symtype=NAME/NUM     symbol type/translation [0-4] (1)\n");
+  fprintf(out, "  -S, --strand=NAME/NUM      query strands to search [1-3] (3)\n");
+  fprintf(out, "  -Q, --query_gencode=NUM    query genetic code [1-23] (1)\n");
+  fprintf(out, "  -D, --db_gencode=NUM       database genetic code [1-23] (1)\n");
+  fprintf(out, "  -H, --show_taxid           show taxid etc in results (no)\n");
+  fprintf(out, "  -o, --out=FILE             output file (stdout)\n");
+  fprintf(out, "  -z, --dbsize=NUM           set effective database size (0)\n");
+}
+
+Options parse_args(int argc, char **argv)
+{
+  Options o;
+  static struct option longopts[] = {
+      {"db", required_argument, nullptr, 'd'}, {"query", required_argument, nullptr, 'i'},
+      {"matrix", required_argument, nullptr, 'M'}, {"penalty", required_argument, nullptr, 'q'},
+      {"reward", required_argument, nullptr, 'r'}, {"gapopen", required_argument, nullptr, 'G'},
+      {"gapextend", required_argument, nullptr, 'E'}, {"strand", required_argument, nullptr, 'S'},
+      {"num_descriptions", required_argument, nullptr, 'v'}, {"num_alignments", required_argument, nullptr, 'b'},
+      {"min_score", required_argument, nullptr, 'c'}, {"max_score", required_argument, nullptr, 'u'},
+      {"evalue", required_argument, nullptr, 'e'}, {"minevalue", required_argument, nullptr, 'k'},
+      {"num_threads", required_argument, nullptr, 'a'}, {"outfmt", required_argument, nullptr, 'm'},
+      {"symtype", required_argument, nullptr, 'p'}, {"taxid", required_argument, nullptr, 'x'},
+      {"comp_based_stats", required_argument, nullptr, 'C'}, {"query_gencode", required_argument, nullptr, 'Q'},
+      {"db_gencode", required_argument, nullptr, 'D'}, {"filter", required_argument, nullptr, 'F'},
+      {"subalignments", required_argument, nullptr, 'K'}, {"dump", required_argument, nullptr, 'N'},
+      {"out", required_argument, nullptr, 'o'}, {"dbsize", required_argument, nullptr, 'z'},
+      {"show_gis", no_argument, nullptr, 'I'}, {"show_taxid", no_argument, nullptr, 'H'},
+      {"help", no_argument, nullptr, 'h'}, {nullptr, 0, nullptr, 0}};
+  int c;
+  while ((c = getopt_long(argc, argv, "d:i:M:q:r:G:E:S:v:b:c:u:e:k:a:m:p:x:C:Q:D:F:K:N:o:z:IHh", longopts, nullptr)) != -1)
+  {
+    switch (c)
+    {
+      case 'a': o.threads = atol(optarg); break;
+      case 'b': o.alignments = atol(optarg); break;
+      case 'c': o.minscore = atol(optarg); break;
+      case 'C':
+        if (strcasecmp(optarg, "F") != 0 && strcmp(optarg, "0") != 0)
+          fatal("Composition-based score adjustments not supported.");
+        break;
+      case 'd': o.databasename = optarg; break;
+      case 'D': o.db_gencode = atol(optarg); break;
+      case 'e': o.expect = atof(optarg); break;
+      case 'E': o.gapextend = atol(optarg); break;
+      case 'F':
+        if (strlen(optarg) != 0 && strcasecmp(optarg, "F") != 0) fatal("Query sequence filtering not supported.");
+        break;
+      case 'G': o.gapopen = atol(optarg); break;
+      case 'h':
+        fprintf(out, "SWIPE-B200 %s\n\nScore-only Smith-Waterman database search on NVIDIA B200, "
+                     "command-line compatible with SWIPE\n(T. Rognes (2011) BMC Bioinformatics, 12:221).\n\n",
+                SWB_CLI_VERSION);
+        usage(argv[0]);
+        exit(1);
+      case 'H': o.show_taxid = 1; break;
+      case 'i': o.queryname = optarg; break;
+      case 'I': o.show_gis = 1; break;
+      case 'k': o.minexpect = atof(optarg); break;
+      case 'K': break;
+      case 'm': o.view = atol(optarg); break;
+      case 'M': o.matrixname = optarg; break;
+      case 'N': fatal("Database dumps (-N) are not supported by this front end.");
+      case 'o': o.outfile = optarg; break;
+      case 'p':
+        if (!strcmp(optarg, "blastn")) o.symtype = 0;
+        else if (!strcmp(optarg, "blastp")) o.symtype = 1;
+        else if (!strcmp(optarg, "blastx")) o.symtype = 2;
+        else if (!strcmp(optarg, "tblastn")) o.symtype = 3;
+        else if (!strcmp(optarg, "tblastx")) o.symtype = 4;
+        else o.symtype = atol(optarg);
+        break;
+      case 'q': o.mismatchscore = atol(optarg); break;
+      case 'Q': o.query_gencode = atol(optarg); break;
+      case 'r': o.matchscore = atol(optarg); break;
+      case 'S':
+        if (!strcmp(optarg, "plus")) o.querystrands = 1;
+        else if (!strcmp(optarg, "minus")) o.querystrands = 2;
+        else if (!strcmp(optarg, "both")) o.querystrands = 3;
+        else o.querystrands = atol(optarg);
+        break;
+      case 'u': o.maxscore = atol(optarg); break;
+      case 'v': o.maxmatches = atol(optarg); break;
+      case 'x': fatal("Taxid lists (-x) are not supported by this front end.");
+      case 'z': o.effdbsize = atol(optarg); break;
+      default:
+        usage(argv[0]);
+        exit(1);
+    }
+  }
+  if (o.outfile)
+  {
+    FILE *f = fopen(o.outfile, "w");
+    if (!f) fatal("Unable to open output file for writing.");
+    out = f;
+  }
+  // defaults that depend on the scoring system (swipe.cc:1089-1126)
+  if (o.symtype == 0)
+  {
+    if (o.gapopen == 0) o.gapopen = 5;
+    if (o.gapextend == 0) o.gapextend = 2;
+  }
+  else if (o.symtype < 5)
+  {
+    if (o.matrixname.empty()) o.matrixname = "BLOSUM62";
+    int64_t go = 0, ge = 0;
+    if (swb_stats_default_gaps(o.matrixname.c_str(), &go, &ge))
+    {
+      if (o.gapopen == 0) o.gapopen = go;
+      if (o.gapextend == 0) o.gapextend = ge;
+    }
+    else if (o.gapopen == 0 && o.gapextend == 0)
+      fatal("Unknown score matrix. Gap penalties must be specified (-G and -E).");
+  }
+  if (o.effdbsize < 0) fatal("Illegal effective db size specified");
+  if (o.threads < 1 || o.threads > 256) fatal("Illegal number of threads specified");
+  if (o.databasename.empty()) fatal("No database specified.");
+  if (!(o.view == 0 || o.view == 7 || o.view == 8 || o.view == 9)) fatal("Illegal view type.");
+  if (o.gapopen < 0 || o.gapextend < 0 || o.gapopen + o.gapextend < 1) fatal("Illegal gap penalties.");
+  if (o.symtype < 0 || o.symtype > 4) fatal("Illegal symbol type.");
+  if (o.querystrands < 1 || o.querystrands > 3) fatal("Illegal query strands specified.");
+  if (o.querystrands == 2 && (o.symtype == 1 || o.symtype == 3 || o.symtype == 4))
+    fatal("Illegal strand specified for protein query.");
+  if (o.query_gencode < 1 || o.query_gencode > 23 || !swb_gencode_name((int)o.query_gencode))
+    fatal("Illegal query genetic code specified.");
+  if (o.db_gencode < 1 || o.db_gencode > 23 || !swb_gencode_name((int)o.db_gencode))
+    fatal("Illegal database genetic code specified.");
+  return o;
+}
+
+// ---- the query and its variants -----------------------------------------------------------------
+struct Query
+{
+  std::string description;
+  std::vector<uint8_t> nt[2];          // forward / reverse complement (symtype 0, 2, 4)
+  std::vector<uint8_t> aa[6];          // [3 * strand + frame]; aa[0] = the query for symtype 1, 3
+};
+
+struct Hit
+{
+  int64_t seqno = 0, score = 0;
+  int qstrand = 0, qframe = 0, dstrand = 0, dframe = 0;
+  int64_t bestq = -1, align_hint = -1;
+  std::string header;                   // raw ASN.1 defline bytes
+  std::vector<uint8_t> dseq;
+  int64_t dlen = 0, dlennt = 0;
+  int64_t aqs = 0, aqe = 0, ads = 0, ade = 0, score_align = 0;
+  std::string ops;
+};
+
+// (score desc, seqno desc, then the order the reference's loops enter equal hits: hits.cc:188-191)
+bool hit_before(const Hit &a, const Hit &b)
+{
+  if (a.score != b.score) return a.score > b.score;
+  if (a.seqno != b.seqno) return a.seqno > b.seqno;
+  if (a.qstrand != b.qstrand) return a.qstrand < b.qstrand;
+  if (a.qframe != b.qframe) return a.qframe < b.qframe;
+  if (a.dstrand != b.dstrand) return a.dstrand < b.dstrand;
+  return a.dframe < b.dframe;
+}
+
+struct Shard
+{
+  int device = 0;
+  int64_t first = 0, count = 0;         // source sequences of the BLAST database
+  swb_db *db = nullptr;
+};
+
+struct Run
+{
+  Options o;
+  swb_blastdb *bdb = nullptr;
+  int64_t nseq = 0, symcount = 0, longest = 0;
+  bool db_nt = false, translated_db = false;
+  int64_t matrix[1024];
+  uint8_t qtable[4096], dtable[4096];
+  swb_stats st;
+  std::vector<Shard> shards;
+  std::vector<Hit> hits;
+  int64_t keephits = 0;
+  std::mutex mu;
+};
+
+const std::vector<uint8_t> &query_variant(const Run &R, const Query &q, int qstrand, int qframe)
+{
+  if (R.o.symtype == 0) return q.nt[qstrand];
+  return q.aa[3 * qstrand + qframe];
+}
+
+void merge_hits(Run &R, std::vector<Hit> &local)
+{
+  std::lock_guard<std::mutex> g(R.mu);
+  R.hits.insert(R.hits.end(), local.begin(), local.end());
+  if ((int64_t)R.hits.size() > R.keephits)
+  {
+    std::sort(R.hits.begin(), R.hits.end(), hit_before);
+    R.hits.resize((size_t)R.keephits);
+  }
+}
+
+// one GPU's share of search_chunk: every query strand / frame against every subject of the shard
+void search_shard(Run &R, const Query &q, Shard &S)
+{
+  const Options &o = R.o;
+  const int unit = R.translated_db ? 6 : 1;
+  const int64_t nsub = S.count * unit;
+  std::vector<int64_t> scores((size_t)std::max<int64_t>(nsub, 1));
+  swb_scoring sc = {R.matrix, o.gapopen + o.gapextend, o.gapextend};
+  const int qs1 = (o.symtype == 0 || o.symtype == 2 || o.symtype == 4) ? (o.querystrands == 2 ? 1 : 0) : 0;
+  const int qs2 = (o.symtype == 0 || o.symtype == 2 || o.symtype == 4) ? (o.querystrands == 1 ? 0 : 1) : 0;
+  const int qf2 = (o.symtype == 2 || o.symtype == 4) ? 2 : 0;
+  std::vector<Hit> local;
+  for (int qstrand = qs1; qstrand <= qs2; qstrand++)
+    for (int qframe = 0; qframe <= qf2; qframe++)
+    {
+      const std::vector<uint8_t> &qv = query_variant(R, q, qstrand, qframe);
+      check(swb_search(S.db, qv.data(), (int64_t)qv.size(), &sc, scores.data(), nullptr), "search");
+      int64_t threshold = R.st.score_threshold;
+      for (int64_t j = 0; j < nsub; j++)
+      {
+        const int64_t s = scores[(size_t)j];
+        if (s < threshold || s > R.st.upper_threshold) continue;
+        const int64_t seqno = S.first + j / unit;
+        if (!swb_blastdb_included(R.bdb, seqno)) continue;
+        Hit h;
+        h.seqno = seqno;
+        h.score = s;
+        if (o.symtype == 0 && qstrand) { h.qstrand = 0; h.dstrand = 1; }     // swipe.cc:1470-1471
+        else
+        {
+          h.qstrand = qstrand; h.qframe = qframe;
+          h.dstrand = unit == 6 ? (int)(j % 6) / 3 : 0;
+          h.dframe = unit == 6 ? (int)(j % 3) : 0;
+        }
+        local.push_back(h);
+        if ((int64_t)local.size() >= 4 * R.keephits + 1024)
+        {
+          std::sort(local.begin(), local.end(), hit_before);
+          local.resize((size_t)R.keephits);
+          threshold = std::max(threshold, local.back().score);   // hits_enter: the list is full (hits.cc:218-219)
+        }
+      }
+    }
+  std::sort(local.begin(), local.end(), hit_before);
+  if ((int64_t)local.size() > R.keephits) local.resize((size_t)R.keephits);
+  merge_hits(R, local);
+}
+
+// the subject as the aligner sees it (hits_align, hits.cc:562-571): strand / frame applied
+void fetch_subject(Run &R, Hit &h)
+{
+  const int64_t n = swb_blastdb_seqlen(R.bdb, h.seqno);
+  std::vector<uint8_t> raw((size_t)std::max<int64_t>(n, 1));
+  int64_t got = 0;
+  const int strand = (R.o.symtype == 0) ? h.dstrand : 0;
+  check(swb_blastdb_sequence(R.bdb, h.seqno, strand, raw.data(), n, &got), "reading a database sequence");
+  if (R.translated_db)
+  {
+    h.dlennt = got;
+    std::vector<uint8_t> prot((size_t)std::max<int64_t>(got / 3 + 1, 1));
+    const int64_t plen = swb_translate(raw.data(), got, h.dstrand, h.dframe, R.dtable, prot.data());
+    prot.resize((size_t)plen);
+    h.dseq.swap(prot);
+  }
+  else
+  {
+    raw.resize((size_t)got);
+    h.dseq.swap(raw);
+  }
+  h.dlen = (int64_t)h.dseq.size();
+}
+
+// align_chunk + hits_align: end cells from the GPU, traceback on the host
+void align_hits(Run &R, const Query &q)
+{
+  const Options &o = R.o;
+  const int64_t nalign = std::min<int64_t>((int64_t)R.hits.size(), o.alignments);
+  int64_t lo = 0, hi = 0, l7 = 0, limit16 = 0;
+  swb_matrix_limits(R.matrix, &lo, &hi, &l7, &limit16);
+  swb_scoring sc = {R.matrix, o.gapopen + o.gapextend, o.gapextend};
+  const int unit = R.translated_db ? 6 : 1;
+  for (const Shard &S : R.shards)
+    for (int qv = 0; qv < 6; qv++)
+    {
+      std::vector<int64_t> list, idx;
+      for (int64_t i = 0; i < nalign; i++)
+      {
+        const Hit &h = R.hits[(size_t)i];
+        if (3 * h.qstrand + h.qframe != qv || h.seqno < S.first || h.seqno >= S.first + S.count) continue;
+        int64_t local = (h.seqno - S.first) * unit;
+        int64_t code;
+        if (unit == 6) code = (local + 3 * h.dstrand + h.dframe) << 3;
+        else code = (local << 3) | ((int64_t)h.dstrand << 2);
+        list.push_back(code);
+        idx.push_back(i);
+      }
+      if (list.empty()) continue;
+      const std::vector<uint8_t> &qq = query_variant(R, q, qv / 3, qv % 3);
+      std::vector<int64_t> s(list.size()), bp(list.size()), bq(list.size());
+      check(swb_search_end(S.db, qq.data(), (int64_t)qq.size(), &sc, list.data(), (int64_t)list.size(),
+                           s.data(), bp.data(), bq.data()), "alignment end search");
+      for (size_t k = 0; k < list.size(); k++)
+        if (s[k] < limit16)                                   // swipe.cc:401-402
+        {
+          R.hits[(size_t)idx[k]].bestq = bq[k];
+          R.hits[(size_t)idx[k]].align_hint = bp[k];
+        }
+    }
+  for (size_t i = 0; i < R.hits.size(); i++)
+  {
+    Hit &h = R.hits[i];
+    const uint8_t *hp = nullptr;
+    int64_t hl = 0;
+    check(swb_blastdb_header(R.bdb, h.seqno, &hp, &hl), "reading a database header");
+    h.header.assign((const char *)hp, (size_t)hl);
+    if ((int64_t)i >= o.alignments) continue;
+    fetch_subject(R, h);
+    const std::vector<uint8_t> &qq = (o.symtype == 0) ? q.nt[0] : q.aa[3 * h.qstrand + h.qframe];
+    if (h.bestq > 0 && h.align_hint != 0)                     // hits.cc:589-600
+    {
+      h.score_align = h.score; h.aqe = h.bestq; h.ade = h.align_hint;
+    }
+    else
+    {
+      h.score_align = 0; h.aqe = 0; h.ade = 0;
+    }
+    std::vector<char> ops(16 * (qq.size() + h.dseq.size()) + 64);
+    int64_t n = 0;
+    const int rc = swb_align(qq.data(), (int64_t)qq.size(), h.dseq.data(), h.dlen, R.matrix, o.gapopen,
+                             o.gapextend, &h.aqs, &h.ads, &h.aqe, &h.ade, &h.score_align, ops.data(),
+                             (int64_t)ops.size(), &n);
+    if (rc != SWB_OK) fatal("Internal error in align function.");
+    h.ops.assign(ops.data(), (size_t)n);
+  }
+}
+
+// ---- report -----------------------------------------------------------------------------------------
+// show_deflines (asnparse.cc:889-971)
+void show_header(const Run &R, const Hit &h, long show_gis, long indent, size_t maxlen, long linelen,
+                 long maxdeflines, bool show_descr)
+{
+  int64_t need = 0;
+  std::vector<char> buf(h.header.size() * 4 + 4096);
+  int64_t n = swb_defline_text((const uint8_t *)h.header.data(), (int64_t)h.header.size(), (int)show_gis,
+                               (int)R.o.show_taxid, 0, buf.data(), (int64_t)buf.size(), &need);
+  if (n == SWB_ERR_RANGE)
+  {
+    buf.resize((size_t)need + 1);
+    n = swb_defline_text((const uint8_t *)h.header.data(), (int64_t)h.header.size(), (int)show_gis,
+                         (int)R.o.show_taxid, 0, buf.data(), (int64_t)buf.size(), &need);
+  }
+  if (n < 0) fatal("Error parsing binary ASN.1 in database sequence definition.");
+  std::vector<std::string> lines;
+  {
+    std::string all(buf.data());
+    size_t p = 0;
+    for (int64_t k = 0; k < n; k++)
+    {
+      size_t e = all.find('\n', p);
+      if (e == std::string::npos) e = all.size();
+      lines.push_back(all.substr(p, e - p));
+      p = e + 1;
+    }
+  }
+  for (size_t x = 0; x < lines.size() && (long)x < maxdeflines; x++)
+  {
+    std::string d = lines[x];
+    size_t show = d.size();
+    if (maxlen && show > maxlen) show = maxlen;
+    if (show < d.size() && show >= 3) d.replace(show - 3, 3, "...");
+    size_t pos = 0;
+    long line = 0;
+    while (pos < show)
+    {
+      long col = 0;
+      if (maxdeflines > 1)
+      {
+        if (line)
+          while (col < 1 + indent) { putc(' ', out); col++; }
+        else { putc(x ? ' ' : '>', out); col++; }
+      }
+      while (pos < show && col < linelen)
+      {
+        const char c = d[pos];
+        if (!show_descr && c == ' ') pos = show;
+        else { putc(c, out); pos++; col++; }
+      }
+      if (linelen < LONG_MAX)
+        while (col < linelen) { putc(' ', out); col++; }
+      if (maxdeflines > 1) putc('\n', out);
+      line++;
+    }
+  }
+}
+
+struct AlignView
+{
+  long identities = 0, positives = 0, indels = 0, aligned = 0, gaps = 0;
+  long q_first = 0, q_last = 0, d_first = 0, d_last = 0;
+  int poswidth = 1;
+  std::string qline, aline, dline, opline;       // one character per alignment column
+};
+
+// count_align / whole_align (hits.cc:815-1176)
+AlignView view_alignment(const Run &R, const Query &q, const Hit &h, bool xml_marks)
+{
+  const Options &o = R.o;
+  AlignView v;
+  const char *sym = o.symtype == 0 ? SYM_NT : SYM_AA;
+  const std::vector<uint8_t> &qs = o.symtype == 0 ? q.nt[h.qstrand] : q.aa[3 * h.qstrand + h.qframe];
+  int64_t qp = h.aqs, dp = h.ads;
+  const char *p = h.ops.c_str();
+  while (*p)
+  {
+    const char op = *p++;
+    long len = 0;
+    int used = 0;
+    sscanf(p, "%ld%n", &len, &used);
+    p += used;
+    v.aligned += len;
+    v.opline.append((size_t)len, op);
+    for (long j = 0; j < len; j++)
+    {
+      if (op == 'D')
+      {
+        v.qline += sym[qs[(size_t)qp++]]; v.aline += ' '; v.dline += '-';
+      }
+      else if (op == 'I')
+      {
+        v.qline += '-'; v.aline += ' '; v.dline += sym[h.dseq[(size_t)dp++]];
+      }
+      else
+      {
+        const int a = qs[(size_t)qp++], b = h.dseq[(size_t)dp++];
+        v.qline += sym[a];
+        v.dline += sym[b];
+        if (a == b)
+        {
+          v.identities++; v.positives++;
+          v.aline += xml_marks || o.symtype == 0 ? '|' : sym[a];
+        }
+        else if (R.matrix[32 * a + b] > 0)
+        {
+          v.positives++;
+          v.aline += o.symtype == 0 && !xml_marks ? ' ' : '+';
+        }
+        else
+          v.aline += ' ';
+      }
+    }
+    if (op != 'M') { v.gaps++; v.indels += len; }
+  }
+  long qf = h.aqs, ql = h.aqe, df = h.ads, dl = h.ade;
+  const long qlen = (long)qs.size(), qlen_nt = (long)q.nt[0].size();
+  if (o.symtype == 0)
+  {
+    if (h.qstrand) { qf = qlen - 1 - qf; ql = qlen - 1 - ql; }
+    if (h.dstrand) { df = h.dlen - 1 - df; dl = h.dlen - 1 - dl; }
+  }
+  if (o.symtype == 2 || o.symtype == 4)
+  {
+    if (h.qstrand) { qf = qlen_nt - 1 - 3 * qf - h.qframe; ql = qlen_nt - 1 - 3 * ql - h.qframe - 2; }
+    else { qf = 3 * qf + h.qframe; ql = 3 * ql + h.qframe + 2; }
+  }
+  if (o.symtype == 3 || o.symtype == 4)
+  {
+    if (h.dstrand) { df = h.dlennt - 1 - 3 * df - h.dframe; dl = h.dlennt - 1 - 3 * dl - h.dframe - 2; }
+    else { df = 3 * df + h.dframe; dl = 3 * dl + h.dframe + 2; }
+  }
+  v.q_first = qf + 1; v.q_last = ql + 1; v.d_first = df + 1; v.d_last = dl + 1;
+  long maxpos = std::max(std::max(v.q_first, v.q_last), std::max(v.d_first, v.d_last));
+  while (maxpos > 9) { maxpos /= 10; v.poswidth++; }
+  return v;
+}
+
+void show_expect(double e)
+{
+  char temp[32];
+  if (e < 1e-180) fprintf(out, "0.0  ");
+  else if (e < 9.5e-100) { snprintf(temp, sizeof temp, "%-6.0e", e); fputs(temp + 1, out); }
+  else if (e < 0.00095) fprintf(out, "%-5.0e", e);
+  else if (e < 0.0995) fprintf(out, "%-5.3f", e);
+  else if (e < 0.95) fprintf(out, "%-5.2f", e);
+  else if (e < 9.5) fprintf(out, "%-5.1f", e);
+  else fprintf(out, "%5.0f", e);
+}
+
+// show_align / putalignop (hits.cc:647-813): 60 columns per block
+void show_alignment_blocks(const Run &R, const Query &q, const Hit &h, const AlignView &v)
+{
+  const Options &o = R.o;
+  const long qlen_nt = (long)q.nt[0].size();
+  long qpos = h.aqs, dpos = h.ads;
+  const size_t total = v.qline.size();
+  for (size_t at = 0; at < total; at += 60)
+  {
+    const size_t n = std::min<size_t>(60, total - at);
+    const long qstart = qpos, dstart = dpos;
+    for (size_t k = 0; k < n; k++)
+    {
+      if (v.opline[at + k] != 'I') qpos++;
+      if (v.opline[at + k] != 'D') dpos++;
+    }
+    long q1 = qstart + 1, q2 = qpos, d1 = dstart + 1, d2 = dpos;
+    if (o.symtype == 0 && h.dstrand) { d1 = h.dlen - d1 + 1; d2 = h.dlen - d2 + 1; }
+    if (o.symtype == 2 || o.symtype == 4)
+    {
+      if (h.qstrand) { q1 = qlen_nt - 3 * qstart - h.qframe; q2 = qlen_nt - 3 * qpos - h.qframe + 1; }
+      else { q1 = 3 * qstart + h.qframe + 1; q2 = 3 * qpos + h.qframe; }
+    }
+    if (o.symtype == 3 || o.symtype == 4)
+    {
+      if (h.dstrand) { d1 = h.dlennt - 3 * dstart - h.dframe; d2 = h.dlennt - 3 * dpos - h.dframe + 1; }
+      else { d1 = 3 * dstart + h.dframe + 1; d2 = 3 * dpos + h.dframe; }
+    }
+    fprintf(out, "\n");
+    fprintf(out, "Query: %*ld %s %ld\n", v.poswidth, q1, v.qline.substr(at, n).c_str(), q2);
+    fprintf(out, "       %*s %s\n", v.poswidth, "", v.aline.substr(at, n).c_str());
+    fprintf(out, "Sbjct: %*ld %s %ld\n", v.poswidth, d1, v.dline.substr(at, n).c_str(), d2);
+  }
+}
+
+void show_description_word(const std::string &d)
+{
+  for (char c : d)
+  {
+    if (c == ' ') break;
+    putc(c, out);
+  }
+}
+
+void report_plain(Run &R, const Query &q, long showalignments, long showhits)
+{
+  const Options &o = R.o;
+  if (R.hits.empty())
+  {
+    fprintf(out, "\nNo hits.\n");
+    return;
+  }
+  if (R.st.available)
+  {
+    fprintf(out, "                                                                 Score    E\n");
+    fprintf(out, "Sequences producing significant alignments:                      (bits) Value\n\n");
+  }
+  else
+    fprintf(out, "Sequences producing significant alignments:                         Score\n\n");
+  for (long i = 0; i < showhits; i++)
+  {
+    const Hit &h = R.hits[(size_t)i];
+    long headerlen = 67;
+    if (o.symtype == 0) headerlen = 65;
+    else if (o.symtype == 2 || o.symtype == 3) headerlen = 64;
+    else if (o.symtype == 4) headerlen = 61;
+    show_header(R, h, o.show_gis, 0, (size_t)headerlen, headerlen, 1, true);
+    if (o.symtype == 0) fprintf(out, " %c", h.dstrand ? '-' : '+');
+    else if (o.symtype == 2) fprintf(out, " %c%d", h.qstrand ? '-' : '+', h.qframe + 1);
+    else if (o.symtype == 3) fprintf(out, " %c%d", h.dstrand ? '-' : '+', h.dframe + 1);
+    else if (o.symtype == 4)
+      fprintf(out, " %c%d/%c%d", h.qstrand ? '-' : '+', h.qframe + 1, h.dstrand ? '-' : '+', h.dframe + 1);
+    if (R.st.available)
+    {
+      const long bits = (long)floor(swb_stats_bits(&R.st, h.score) + 0.5);
+      fprintf(out, " %5ld", bits);
+      fprintf(out, "   ");
+      show_expect(swb_stats_evalue(&R.st, h.score));
+    }
+    else
+      fprintf(out, " %5ld", (long)h.score);
+    putc('\n', out);
+  }
+  for (long i = 0; i < showalignments; i++)
+  {
+    const Hit &h = R.hits[(size_t)i];
+    fprintf(out, "\n");
+    show_header(R, h, o.show_gis, 10, 0, 79, LONG_MAX, true);
+    fprintf(out, "          Length = %ld\n", (long)((o.symtype == 3 || o.symtype == 4) ? h.dlennt : h.dlen));
+    fprintf(out, "\n");
+    if (R.st.available)
+    {
+      fprintf(out, " Score = %.1lf bits (%ld), Expect = ", swb_stats_bits(&R.st, h.score), (long)h.score);
+      show_expect(swb_stats_evalue(&R.st, h.score));
+    }
+    else
+      fprintf(out, " Score = %ld", (long)h.score);
+    putc('\n', out);
+    const AlignView v = view_alignment(R, q, h, false);
+    fprintf(out, " Identities = %ld/%ld (%ld%%)", v.identities, v.aligned, v.identities * 100 / v.aligned);
+    if (o.symtype > 0)
+      fprintf(out, ", Positives = %ld/%ld (%ld%%)", v.positives, v.aligned, v.positives * 100 / v.aligned);
+    if (v.indels) fprintf(out, ", Gaps = %ld/%ld (%ld%%)", v.indels, v.aligned, v.indels * 100 / v.aligned);
+    fprintf(out, "\n");
+    if (o.symtype == 0) fprintf(out, " Strand = %s\n", h.dstrand ? "Plus / Minus" : "Plus / Plus");
+    else if (o.symtype == 2) fprintf(out, " Frame = %c%d\n", h.qstrand ? '-' : '+', h.qframe + 1);
+    else if (o.symtype == 3) fprintf(out, " Frame = %c%d\n", h.dstrand ? '-' : '+', h.dframe + 1);
+    else if (o.symtype == 4)
+      fprintf(out, " Frame = %c%d / %c%d\n", h.qstrand ? '-' : '+', h.qframe + 1, h.dstrand ? '-' : '+', h.dframe + 1);
+    show_alignment_blocks(R, q, h, v);
+    fprintf(out, "\n");
+  }
+}
+
+void report_xml(Run &R, const Query &q, long showalignments, long showhits)
+{
+  fprintf(out, "<result>\n  <general>\n    <hitcount>%d</hitcount>\n  </general>\n  <hits>\n", (int)R.hits.size());
+  for (long i = 0; i < showhits; i++)
+  {
+    const Hit &h = R.hits[(size_t)i];
+    fprintf(out, "    <hit>\n      <hitno>%ld</hitno>\n      <track>%ld</track>\n      <query>", i + 1, (long)h.seqno);
+    show_description_word(q.description);
+    fprintf(out, "</query>\n      <name>");
+    show_header(R, h, R.o.show_gis, 0, 0, LONG_MAX, 1, true);
+    fprintf(out, "</name>\n      <len>%ld</len>\n      <score>%ld</score>\n", (long)h.dlen, (long)h.score);
+    if (i < showalignments)
+    {
+      const AlignView v = view_alignment(R, q, h, true);
+      fprintf(out, "      <alignment>%s</alignment>\n", h.ops.c_str());
+      fprintf(out, "      <qpos>%ld,%ld</qpos>\n      <dpos>%ld,%ld</dpos>\n", v.q_first, v.q_last, v.d_first, v.d_last);
+      fprintf(out, "      <qseq>%s</qseq>\n      <aseq>%s</aseq>\n      <dseq>%s</dseq>\n", v.qline.c_str(),
+              v.aline.c_str(), v.dline.c_str());
+    }
+    fprintf(out, "    </hit>\n");
+  }
+  fprintf(out, "  </hits>\n</result>\n");
+}
+
+void report_tsv(Run &R, const Query &q, long showalignments, bool comments)
+{
+  if (comments)
+  {
+    fprintf(out, "# SWIPE-B200 %s - score-only Smith-Waterman scan on NVIDIA B200, SWIPE-compatible output "
+                 "(T. Rognes (2011) BMC Bioinformatics, 12:221).\n", SWB_CLI_VERSION);
+    fprintf(out, "# Query: %s\n", q.description.c_str());
+    fprintf(out, "# Database: %s\n", R.o.databasename.c_str());
+    if (R.st.available)
+      fprintf(out, "# Fields: Query id, Subject id, %% identity, alignment length, mismatches, gap openings, q. start, q. end, s. start, s. end, e-value, bit score\n");
+    else
+      fprintf(out, "# Fields: Query id, Subject id, %% identity, alignment length, mismatches, gap openings, q. start, q. end, s. start, s. end, score\n");
+  }
+  for (long i = 0; i < showalignments; i++)
+  {
+    const Hit &h = R.hits[(size_t)i];
+    show_description_word(q.description);
+    putc('\t', out);
+    show_header(R, h, 1, 0, 0, LONG_MAX, 1, false);
+    const AlignView v = view_alignment(R, q, h, false);
+    fprintf(out, "\t%.2f\t%ld\t%ld\t%ld\t%ld\t%ld\t%ld\t%ld", 100.0 * v.identities / v.aligned, v.aligned,
+            v.aligned - v.identities - v.indels, v.gaps, v.q_first, v.q_last, v.d_first, v.d_last);
+    if (R.st.available)
+      fprintf(out, "\t%.2g\t%.1f", swb_stats_evalue(&R.st, h.score), swb_stats_bits(&R.st, h.score));
+    else
+      fprintf(out, "\t%ld", (long)h.score);
+    fprintf(out, "\n");
+  }
+}
+
+void show_run_header(const Run &R, const Query &q)
+{
+  const Options &o = R.o;
+  static const char *const symtypes[] = {"Nucleotide", "Amino acid", "Translated query", "Translated database",
+                                         "Both translated"};
+  fprintf(out, "Database file:     %s\n", o.databasename.c_str());
+  fprintf(out, "Database title:    %s\n", swb_blastdb_title(R.bdb));
+  fprintf(out, "Database time:     %s\n", swb_blastdb_date(R.bdb));
+  fprintf(out, "Database size:     %ld residues in %ld sequences\n", (long)R.symcount, (long)R.nseq);
+  fprintf(out, "Longest db seq:    %ld residues\n", (long)R.longest);
+  if (o.effdbsize > 0) fprintf(out, "Effecive db size:  %ld\n", o.effdbsize);
+  fprintf(out, "Query file name:   %s\n", o.queryname.c_str());
+  const long qlen = (o.symtype == 0 || o.symtype == 2 || o.symtype == 4) ? (long)q.nt[0].size() : (long)q.aa[0].size();
+  fprintf(out, "Query length:      %ld residues\n", qlen);
+  for (size_t i = 0; i < q.description.size(); i += 60)
+    fprintf(out, "%s%-60.60s\n", i ? "                   " : "Query description: ", q.description.c_str() + i);
+  if (o.symtype == 0)
+  {
+    static const char *const strands[] = {"", "Plus", "Minus", "Plus and minus"};
+    fprintf(out, "Query strands:     %s\n", strands[o.querystrands]);
+    fprintf(out, "Score matrix:      %ld/%ld\n", o.matchscore, o.mismatchscore);
+  }
+  else
+    fprintf(out, "Score matrix:      %s\n", o.matrixname.c_str());
+  fprintf(out, "Gap penalty:       %ld+%ldk\n", o.gapopen, o.gapextend);
+  fprintf(out, "Max expect shown:  %-g\n", o.expect);
+  fprintf(out, "Min score shown:   %ld\n", o.minscore);
+  fprintf(out, "Max matches shown: %ld\n", o.maxmatches);
+  fprintf(out, "Alignments shown:  %ld\n", o.alignments);
+  fprintf(out, "Show gi's:         %ld\n", o.show_gis);
+  fprintf(out, "Show taxid's:      %ld\n", o.show_taxid);
+  fprintf(out, "Threads:           %ld\n", o.threads);
+  fprintf(out, "Symbol type:       %s\n", symtypes[o.symtype]);
+  if (o.symtype == 2 || o.symtype == 4)
+    fprintf(out, "Query genetic code:%s (%ld)\n", swb_gencode_name((int)o.query_gencode), o.query_gencode);
+  if (o.symtype == 3 || o.symtype == 4)
+    fprintf(out, "DB genetic code:   %s (%ld)\n", swb_gencode_name((int)o.db_gencode), o.db_gencode);
+  fprintf(out, "\n");
+}
+
+void build_query(Run &R, Query &q, std::vector<uint8_t> &seq)
+{
+  const Options &o = R.o;
+  for (auto &v : q.nt) v.clear();
+  for (auto &v : q.aa) v.clear();
+  if (o.symtype == 0 || o.symtype == 2 || o.symtype == 4)
+  {
+    q.nt[0] = seq;
+    if (o.querystrands & 2)
+    {
+      q.nt[1].resize(seq.size());
+      swb_revcomp(seq.data(), (int64_t)seq.size(), q.nt[1].data());
+    }
+    if (o.symtype != 0)
+      for (int s = 0; s < 2; s++)
+        if ((s + 1) & o.querystrands)
+          for (int f = 0; f < 3; f++)
+          {
+            q.aa[3 * s + f].resize(seq.size() / 3 + 1);
+            const int64_t n = swb_translate(seq.data(), (int64_t)seq.size(), s, f, R.qtable, q.aa[3 * s + f].data());
+            q.aa[3 * s + f].resize((size_t)std::max<int64_t>(n, 0));
+          }
+  }
+  else
+    q.aa[0] = seq;
+}
+
+void work(Run &R, Query &q)
+{
+  const Options &o = R.o;
+  if (o.view == 0) show_run_header(R, q);
+  // hits_init (hits.cc:283-511)
+  R.keephits = std::max(o.maxmatches, o.alignments);
+  int64_t maxhits = R.nseq;
+  if (o.symtype == 0) maxhits *= o.querystrands == 3 ? 2 : 1;
+  else if (o.symtype == 2) maxhits *= o.querystrands == 3 ? 6 : 3;
+  else if (o.symtype == 3) maxhits *= 6;
+  else if (o.symtype == 4) maxhits *= o.querystrands == 3 ? 36 : 18;
+  R.keephits = std::min(R.keephits, maxhits);
+  const int64_t qlen = (o.symtype == 0 || o.symtype == 2 || o.symtype == 4) ? (int64_t)q.nt[0].size() : (int64_t)q.aa[0].size();
+  check(swb_stats_init((int)o.symtype, o.matrixname.c_str(), o.matchscore, o.mismatchscore, o.gapopen,
+                       o.gapextend, qlen, R.symcount, R.nseq, o.effdbsize, o.minscore, o.maxscore, o.expect,
+                       o.minexpect, &R.st), "statistics");
+  if (!R.st.available && o.view == 0)
+    fprintf(out, "Statistical parameters are not available for the scoring system specified.\nBit scores and E-values will not be computed.\n\n");
+  R.hits.clear();
+  if (o.view == 0)
+  {
+    fprintf(out, "Searching...");
+    fflush(out);
+  }
+  struct tms t1, t2;
+  const time_t w1 = time(nullptr);
+  const clock_t c1 = times(&t1);
+  {
+    std::vector<std::thread> pool;
+    for (Shard &S : R.shards) pool.emplace_back([&R, &q, &S]() { search_shard(R, q, S); });
+    for (std::thread &t : pool) t.join();
+  }
+  std::sort(R.hits.begin(), R.hits.end(), hit_before);
+  if ((int64_t)R.hits.size() > R.keephits) R.hits.resize((size_t)R.keephits);
+  const clock_t c2 = times(&t2);
+  const time_t w2 = time(nullptr);
+  if (o.view == 0)
+  {
+    fprintf(out, "...............................................done\n\n");
+    char b1[40], b2[40];
+    struct tm tmv;
+    gmtime_r(&w1, &tmv); strftime(b1, sizeof b1, "%a, %e %b %Y %T UTC", &tmv);
+    gmtime_r(&w2, &tmv); strftime(b2, sizeof b2, "%a, %e %b %Y %T UTC", &tmv);
+    const double elapsed = (double)(c2 - c1) / (double)sysconf(_SC_CLK_TCK);
+    double speed = (double)R.symcount;
+    if (o.symtype == 0) speed *= (double)q.nt[0].size() * (o.querystrands == 3 ? 2 : 1);
+    else if (o.symtype == 1) speed *= (double)q.aa[0].size();
+    else if (o.symtype == 2) speed *= (double)q.nt[0].size() * (o.querystrands == 3 ? 2 : 1);
+    else if (o.symtype == 3) speed *= 2.0 * (double)q.aa[0].size();
+    else speed *= 2.0 * (double)q.nt[0].size() * (o.querystrands == 3 ? 2 : 1);
+    fprintf(out, "Search started:    %s\n", b1);
+    fprintf(out, "Search completed:  %s\n", b2);
+    fprintf(out, "Elapsed:           %.2fs\n", elapsed);
+    fprintf(out, "Speed:             %.3f GCUPS\n", speed / elapsed / 1e9);
+    fprintf(out, "\n");
+  }
+  align_hits(R, q);
+  const long showhits = (long)std::min<int64_t>((int64_t)R.hits.size(), o.maxmatches);
+  const long showalignments = (long)std::min<int64_t>((int64_t)R.hits.size(), o.alignments);
+  if (o.view == 0) report_plain(R, q, showalignments, showhits);
+  else if (o.view == 7) report_xml(R, q, showalignments, showhits);
+  else report_tsv(R, q, showalignments, o.view == 9);
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+  Run R;
+  R.o = parse_args(argc, argv);
+  const Options &o = R.o;
+  R.db_nt = o.symtype == 0 || o.symtype == 3 || o.symtype == 4;
+  R.translated_db = o.symtype == 3 || o.symtype == 4;
+  check(swb_blastdb_open(o.databasename.c_str(), R.db_nt ? 1 : 0, &R.bdb), "database");
+  int vols = 0;
+  swb_blastdb_info(R.bdb, &R.nseq, &R.symcount, &R.longest, &vols);
+
+  if (o.symtype == 0) swb_matrix_nucleotide(o.matchscore, o.mismatchscore, R.matrix);
+  else
+  {
+    const int rc = swb_matrix_read(o.matrixname.c_str(), R.matrix);
+    if (rc == SWB_ERR_IO) fatal("Cannot open score matrix file.");
+    if (rc != SWB_OK) fatal("Problem parsing score matrix file.");
+  }
+  swb_translate_table((int)o.query_gencode, R.qtable);
+  swb_translate_table((int)o.db_gencode, R.dtable);
+
+  // the database: one shard per GPU, cut by sequence number into equal residue shares
+  int ndev = 0;
+  check(swb_device_count(&ndev), "CUDA");
+  const int ngpu = (int)std::min<long>(o.threads, ndev);
+  {
+    std::vector<int64_t> cum((size_t)R.nseq + 1, 0);
+    for (int64_t s = 0; s < R.nseq; s++) cum[(size_t)s + 1] = cum[(size_t)s] + swb_blastdb_seqlen(R.bdb, s);
+    int64_t first = 0;
+    for (int g = 0; g < ngpu; g++)
+    {
+      const int64_t target = cum[(size_t)R.nseq] * (g + 1) / ngpu;
+      int64_t last = g + 1 == ngpu ? R.nseq
+                                   : (int64_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+      last = std::max(first, std::min(last, R.nseq));
+      Shard S;
+      S.device = g; S.first = first; S.count = last - first;
+      R.shards.push_back(S);
+      first = last;
+    }
+  }
+  {
+    std::vector<std::thread> pool;
+    std::vector<int> rcs(R.shards.size(), 0);
+    for (size_t g = 0; g < R.shards.size(); g++)
+      pool.emplace_back([&R, &rcs, g]() {
+        Shard &S = R.shards[g];
+        rcs[g] = R.translated_db
+                     ? swb_db_open_blast_translated(S.device, R.bdb, S.first, S.count, R.dtable, 0, nullptr, &S.db)
+                     : swb_db_open_blast(S.device, R.bdb, S.first, S.count, 0, nullptr, &S.db);
+      });
+    for (std::thread &t : pool) t.join();
+    for (int rc : rcs) check(rc, "uploading the database");
+  }
+
+  // queries
+  std::string text;
+  {
+    FILE *f = o.queryname == "-" ? stdin : fopen(o.queryname.c_str(), "r");
+    if (!f) fatal("Cannot open query file.");
+    char buf[65536];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+    if (f != stdin) fclose(f);
+  }
+  if (o.view == 0)
+    fprintf(out, "SWIPE-B200 %s\n\nScore-only Smith-Waterman database search on NVIDIA B200, command-line compatible with\n"
+                 "SWIPE: T. Rognes (2011) BMC Bioinformatics, 12:221.\n\n", SWB_CLI_VERSION);
+  else if (o.view == 7)
+    fprintf(out, "<?xml version=\"1.0\"?>\n");
+  const bool nt_query = o.symtype == 0 || o.symtype == 2 || o.symtype == 4;
+  size_t at = 0;
+  while (at < text.size())
+  {
+    std::vector<uint8_t> seq(text.size() - at + 1);
+    std::vector<char> descr(text.size() - at + 2);
+    int64_t n = 0;
+    const int64_t used = swb_query_parse(text.data() + at, (int64_t)(text.size() - at), nt_query ? 1 : 0, seq.data(),
+                                         (int64_t)seq.size(), &n, descr.data(), (int64_t)descr.size());
+    if (used <= 0) break;
+    at += (size_t)used;
+    seq.resize((size_t)n);
+    Query q;
+    q.description = descr.data();
+    build_query(R, q, seq);
+    work(R, q);
+  }
+  for (Shard &S : R.shards) swb_db_close(S.db);
+  swb_blastdb_close(R.bdb);
+  if (o.outfile) fclose(out);
+  return 0;
+}
