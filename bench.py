@@ -305,6 +305,15 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = total_res + 8 * nseq                 # 1 B per residue + 8 B per subject
         achieved = alg_bytes / (scan_avg * 1e-3) * 1e-9
+        # DRAM traffic of the scan kernel from the committed ncu --set full capture, scaled from the
+        # captured shard to this one by algorithmic bytes (the kernel streams every block once)
+        traffic = None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            cap_alg = cap["residues"] + 8 * cap["subjects"]
+            traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * (alg_bytes / cap_alg)
+        except Exception:
+            pass
         sm_mhz = clocks["sm_mhz"] or 1965.0
         cells_per_clk_sm = cells / (scan_avg * 1e-3) / (148 * sm_mhz * 1e6)
         line = {
@@ -314,7 +323,9 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks,
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "traffic_source": "profiles/r1_ncu_traffic.json (ncu capture at 1.5M subjects, scaled by algorithmic bytes)",
+                         "algorithmic_bytes": alg_bytes,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "kernel": "swb_scan_kernel", "kernel_ms": scan_avg,
                          "note": "integer-issue bound, not HBM bound (SURVEY 8d): see alu"},

@@ -14,6 +14,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace
@@ -204,6 +206,7 @@ struct swb_db
   DevBuf<uint4> bndH, bndF;
   DevBuf<ScanSeg> segs;           // chunk table of a merged (whole-shard) scan launch
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_group[2] = {nullptr, nullptr};   // completion of the last two scan launches
   double upload_ms = 0, layout_ms = 0;
   int force_G = 0, force_R = 0, force_mode = -1;   // test hooks (swb_set_shape)
 };
@@ -522,29 +525,50 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
                              cudaMemcpyHostToDevice, st));
     SWB_CUDA(cudaMemcpyAsync(db->qrow_off.p, tb.qrow.data(), tb.qrow.size() * sizeof(unsigned short),
                              cudaMemcpyHostToDevice, st));
-    // One launch per chunk while the shard is still arriving (upload / re-layout / scan overlap);
-    // one launch over all chunks (blockIdx.y = chunk) once every chunk is laid out, so that the SMs
-    // run from one chunk into the next and the ragged end of a launch is paid once per search.
-    bool merged = layouts.size() > 1 && layouts.size() <= 65535;   // gridDim.y limit
-    if (const char *env = getenv("SWB_MERGE")) merged = merged && atoi(env) != 0;
+    // Chunks are scanned in GROUPS of consecutive chunks, one launch per group (blockIdx.y = chunk
+    // of the group), so that the SMs run from one chunk into the next and the ragged end of a launch
+    // is paid once per group.  Resident shard: one group.  Shard still arriving (asynchronous open):
+    // a group is whatever has been laid out by the time the GPU is about to need more work -- at most
+    // two launches are kept in flight -- so upload, re-layout and scan overlap and the launches grow
+    // as the upload gets ahead of the scan.
+    std::vector<Layout *> work;
     for (Layout *L : layouts)
-      if (merged && L->ev_ready && cudaEventQuery(L->ev_ready) != cudaSuccess) merged = false;
+      if (L->n > 0) work.push_back(L);
+    bool merge = work.size() <= 65535;                               // gridDim.y limit
+    if (const char *env = getenv("SWB_MERGE")) merge = merge && atoi(env) != 0;
+    bool resident = true;
+    for (Layout *L : work)
+      if (L->ev_ready && cudaEventQuery(L->ev_ready) != cudaSuccess) resident = false;
     (void)cudaGetLastError();
-    if (merged && !getenv("SWB_OVERSUB")) oversub = layouts.size() >= 4 ? 1 : oversub;
+    if (merge && resident && !getenv("SWB_OVERSUB")) oversub = work.size() >= 4 ? 1 : oversub;
     const int grid = db->sm_count * occ * oversub;
     const int nstreams = grid * SWB_STREAMS;
-    long long max_blocks = 0, sum_blocks = 0;
-    for (Layout *L : layouts)
+    long long sum_blocks = 0;
+    std::vector<ScanSeg> segs(work.size());
+    for (size_t k = 0; k < work.size(); k++)
     {
-      max_blocks = std::max(max_blocks, L->cap_blocks);
+      Layout *L = work[k];
+      if (L->stream_pair_n != nstreams)
+      {
+        SWB_TRY(L->stream_pair.reserve((size_t)nstreams + 1));
+        L->stream_pair_n = -nstreams - 1;                            // reserved, partition still to run
+      }
+      ScanSeg &S = segs[k];
+      S.blocks = L->blocks.p; S.pairblk = L->pairblk.p; S.stream_pair = L->stream_pair.p;
+      S.pair_scores = L->pair_scores.p;
+      S.bnd_base = sum_blocks;
       sum_blocks += L->cap_blocks;
     }
     if (npass > 1)
     {
-      SWB_TRY(db->bndH.reserve((size_t)(merged ? sum_blocks : max_blocks)));
-      SWB_TRY(db->bndF.reserve((size_t)(merged ? sum_blocks : max_blocks)));
+      SWB_TRY(db->bndH.reserve((size_t)sum_blocks));
+      SWB_TRY(db->bndF.reserve((size_t)sum_blocks));
     }
     SWB_TRY(db->requeue.reserve((size_t)n));
+    SWB_TRY(db->segs.reserve(std::max<size_t>(segs.size(), 1)));
+    if (!segs.empty())
+      SWB_CUDA(cudaMemcpyAsync(db->segs.p, segs.data(), segs.size() * sizeof(ScanSeg),
+                               cudaMemcpyHostToDevice, st));
     const long long q = sc->gap_open_extend, r = sc->gap_extend;
     const unsigned nq16 = (unsigned)(unsigned short)enc16(-q, mode);
     const unsigned nr16 = (unsigned)(unsigned short)(short)(-r);
@@ -556,68 +580,53 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     P.bndH = db->bndH.p; P.bndF = db->bndF.p;
     P.nq = tb.nq; P.npass = npass;
     P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
-    std::vector<ScanSeg> segs;
     SWB_CUDA(cudaEventRecord(db->ev[0], st));
-    for (Layout *L : layouts)
+    size_t next = 0;
+    int group_no = 0;
+    while (next < work.size())
     {
-      if (L->n == 0) continue;
-      if (L->ev_ready) SWB_CUDA(cudaStreamWaitEvent(st, L->ev_ready, 0));
-      if (L->stream_pair_n != nstreams)
+      size_t end = next + 1;
+      if (!resident)
       {
-        SWB_TRY(L->stream_pair.reserve((size_t)nstreams + 1));
-        swb_partition_kernel<<<(nstreams + 1 + 255) / 256, 256, 0, st>>>(L->pairblk.p, L->npairs,
-                                                                         nstreams, L->stream_pair.p);
-        SWB_CUDA(cudaGetLastError());
-        launches++;
-        L->stream_pair_n = nstreams;
+        if (group_no >= 2) SWB_CUDA(cudaEventSynchronize(db->ev_group[group_no & 1]));   // group_no - 2 is done
+        if (work[next]->ev_ready) SWB_CUDA(cudaEventSynchronize(work[next]->ev_ready));
       }
-      SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * sizeof(u32), st));
-      ScanSeg S;
-      S.blocks = L->blocks.p; S.pairblk = L->pairblk.p; S.stream_pair = L->stream_pair.p;
-      S.pair_scores = L->pair_scores.p;
-      S.bnd_base = 0;
-      if (merged)
+      if (merge)
+        while (end < work.size() &&
+               (resident || !work[end]->ev_ready || cudaEventQuery(work[end]->ev_ready) == cudaSuccess))
+          end++;
+      (void)cudaGetLastError();
+      for (size_t k = next; k < end; k++)
       {
-        segs.push_back(S);                           // bnd_base is filled in below
-        continue;
+        Layout *L = work[k];
+        if (L->ev_ready) SWB_CUDA(cudaStreamWaitEvent(st, L->ev_ready, 0));
+        if (L->stream_pair_n != nstreams)
+        {
+          swb_partition_kernel<<<(nstreams + 1 + 255) / 256, 256, 0, st>>>(L->pairblk.p, L->npairs,
+                                                                           nstreams, L->stream_pair.p);
+          SWB_CUDA(cudaGetLastError());
+          launches++;
+          L->stream_pair_n = nstreams;
+        }
+        SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * sizeof(u32), st));
       }
-      P.seg = S;
-      fn<<<grid, threads, smem, st>>>(P);
+      P.seg = segs[next];
+      P.segs = db->segs.p + next;
+      fn<<<dim3((unsigned)grid, (unsigned)(end - next)), threads, smem, st>>>(P);
       SWB_CUDA(cudaGetLastError());
       launches++;
-      swb_finish_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(
-          L->pair_scores.p, L->idx_out.p, L->n, L->first, limit, db->scores.p, db->requeue.p,
-          db->counters.p);
-      SWB_CUDA(cudaGetLastError());
-      launches++;
-    }
-    if (merged && !segs.empty())
-    {
-      long long base = 0;
-      size_t k = 0;
-      for (Layout *L : layouts)
+      for (size_t k = next; k < end; k++)
       {
-        if (L->n == 0) continue;
-        segs[k++].bnd_base = base;
-        base += L->cap_blocks;
-      }
-      SWB_TRY(db->segs.reserve(segs.size()));
-      SWB_CUDA(cudaMemcpyAsync(db->segs.p, segs.data(), segs.size() * sizeof(ScanSeg),
-                               cudaMemcpyHostToDevice, st));
-      P.seg = segs[0];
-      P.segs = db->segs.p;
-      fn<<<dim3((unsigned)grid, (unsigned)segs.size()), threads, smem, st>>>(P);
-      SWB_CUDA(cudaGetLastError());
-      launches++;
-      for (Layout *L : layouts)
-      {
-        if (L->n == 0) continue;
+        Layout *L = work[k];
         swb_finish_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(
             L->pair_scores.p, L->idx_out.p, L->n, L->first, limit, db->scores.p, db->requeue.p,
             db->counters.p);
         SWB_CUDA(cudaGetLastError());
         launches++;
       }
+      if (!resident) SWB_CUDA(cudaEventRecord(db->ev_group[group_no & 1], st));
+      group_no++;
+      next = end;
     }
     SWB_CUDA(cudaEventRecord(db->ev[1], st));
     unsigned long long h_nreq = 0;
@@ -800,10 +809,15 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
   const long long *cut_off = S.translate ? S.nt_offsets.data() : offsets;
   std::vector<long long> cut;                       // chunk c covers source sequences [cut[c], cut[c+1])
   cut.push_back(0);
+  // the first chunks are small so that the scan can start while most of the shard is still on the
+  // wire (32, 64, 128 MB, then full size)
+  const bool ramp = getenv("SWB_CHUNK_BYTES") == nullptr;
   while (cut.back() < nsrc)
   {
     const long long lo = cut.back();
-    const long long *e = std::upper_bound(cut_off + lo + 1, cut_off + nsrc + 1, cut_off[lo] + chunk_bytes);
+    long long budget = chunk_bytes;
+    if (ramp && cut.size() <= 3) budget = chunk_bytes >> (4 - cut.size());
+    const long long *e = std::upper_bound(cut_off + lo + 1, cut_off + nsrc + 1, cut_off[lo] + budget);
     long long hi = (long long)(e - cut_off) - 1;     // last boundary within the byte budget
     if (hi <= lo) hi = lo + 1;
     if (nsrc - hi < (hi - lo) / 4) hi = nsrc;        // do not leave a sliver behind
@@ -820,6 +834,7 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
     SWB_CUDA(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
     SWB_CUDA(cudaStreamCreateWithFlags(&db->layout_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; i++) SWB_CUDA(cudaEventCreate(&db->ev[i]));
+    for (int i = 0; i < 2; i++) SWB_CUDA(cudaEventCreateWithFlags(&db->ev_group[i], cudaEventDisableTiming));
     for (int i = 0; i < 3; i++) SWB_CUDA(cudaEventCreate(&db->ev_open[i]));
     SWB_CUDA(cudaEventCreateWithFlags(&db->ev_uploaded, cudaEventDisableTiming));
     SWB_TRY(db->residues.reserve((size_t)offsets[nseq] + 16));
@@ -933,12 +948,38 @@ static int open_raw(int device, const uint8_t *residues, const int64_t *offsets,
   OpenSrc S;
   S.nseq = nseq;
   S.trailing = trailing;
-  for (long long i = 0; i < nseq; i++)
   {
-    const long long len = offsets[i + 1] - offsets[i] - trailing;
-    if (len < 0 || len > 0x7fffffffLL) return SWB_ERR_ARG;
-    S.total += len;
-    S.longest = std::max(S.longest, len);
+    // one pass over the offsets (range check, total, longest), cut over a few host threads when the
+    // shard is large: at 5 M subjects a serial loop costs more host time than enqueueing the upload
+    struct Acc { long long total = 0, longest = 0, shortest = 0; };
+    auto pass = [&](Acc &a, long long lo, long long hi) {
+      long long tot = 0, mx = 0, mn = 0;
+      for (long long i = lo; i < hi; i++)
+      {
+        const long long len = offsets[i + 1] - offsets[i] - trailing;
+        tot += len;
+        mx = len > mx ? len : mx;
+        mn = len < mn ? len : mn;
+      }
+      a.total = tot; a.longest = mx; a.shortest = mn;
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    const long long nt = std::max<long long>(1, std::min<long long>(std::min<long long>(hw ? hw : 1, 8), nseq >> 19));
+    std::vector<Acc> acc((size_t)nt);
+    if (nt == 1) pass(acc[0], 0, nseq);
+    else
+    {
+      std::vector<std::thread> pool;
+      for (long long t = 0; t < nt; t++)
+        pool.emplace_back([&, t]() { pass(acc[(size_t)t], nseq * t / nt, nseq * (t + 1) / nt); });
+      for (std::thread &t : pool) t.join();
+    }
+    for (const Acc &a : acc)
+    {
+      if (a.shortest < 0 || a.longest > 0x7fffffffLL) return SWB_ERR_ARG;
+      S.total += a.total;
+      S.longest = std::max(S.longest, a.longest);
+    }
   }
   S.offsets = (const long long *)offsets;
   if (offsets[0] != 0)                             // rebase so that residues[0] is the first byte uploaded
@@ -1116,6 +1157,8 @@ int swb_db_close(swb_db *db)
     if (db->ev[i]) cudaEventDestroy(db->ev[i]);
   for (int i = 0; i < 3; i++)
     if (db->ev_open[i]) cudaEventDestroy(db->ev_open[i]);
+  for (int i = 0; i < 2; i++)
+    if (db->ev_group[i]) cudaEventDestroy(db->ev_group[i]);
   if (db->ev_uploaded) cudaEventDestroy(db->ev_uploaded);
   if (db->copy_stream) cudaStreamDestroy(db->copy_stream);
   if (db->layout_stream) cudaStreamDestroy(db->layout_stream);
@@ -1168,25 +1211,26 @@ int64_t swb_topk_merge(int nshards, const int64_t *const *scores, const int64_t 
 {
   if (nshards < 0 || keep < 0 || (nshards > 0 && (!scores || !n || !seqno_base))) return SWB_ERR_ARG;
   if (keep > 0 && (!out_seqno || !out_score)) return SWB_ERR_ARG;
+  for (int s = 0; s < nshards; s++)
+    if (n[s] < 0 || (n[s] > 0 && !scores[s])) return SWB_ERR_ARG;
   // hits_enter keeps (score desc, seqno desc) and, once full, only admits scores >= the last
   // kept one; the final list therefore is the top `keep` of the admissible hits in that order,
-  // whatever the arrival order -- which is what makes the multi-GPU merge deterministic.
+  // whatever the arrival order -- which is what makes the multi-GPU merge (and the split of one
+  // shard over host threads below) deterministic.
   struct Hit { int64_t score, seqno; };
-  std::vector<Hit> heap;                       // min-heap on (score, seqno) of the best so far
   auto worse = [](const Hit &a, const Hit &b) {
     return a.score != b.score ? a.score > b.score : a.seqno > b.seqno;
   };
-  int64_t tot = 0, obv = 0;
-  for (int s = 0; s < nshards; s++)
-  {
-    if (n[s] < 0 || (n[s] > 0 && !scores[s])) return SWB_ERR_ARG;
-    for (int64_t i = 0; i < n[s]; i++)
+  struct Part { std::vector<Hit> heap; int64_t tot = 0, obv = 0; };
+  auto scan = [&](Part &P, const int64_t *sc, int64_t lo, int64_t hi, int64_t base) {
+    std::vector<Hit> &heap = P.heap;                 // min-heap on (score, seqno) of the best so far
+    for (int64_t i = lo; i < hi; i++)
     {
-      const int64_t sc = scores[s][i];
-      if (sc > upper_score) obv++;
-      if (sc >= min_score) tot++;
-      if (sc < min_score || sc > upper_score || keep == 0) continue;
-      const Hit h = {sc, seqno_base[s] + i};
+      const int64_t v = sc[i];
+      if (v > upper_score) P.obv++;
+      if (v >= min_score) P.tot++;
+      if (v < min_score || v > upper_score || keep == 0) continue;
+      const Hit h = {v, base + i};
       if ((int64_t)heap.size() < keep)
       {
         heap.push_back(h);
@@ -1199,16 +1243,54 @@ int64_t swb_topk_merge(int nshards, const int64_t *const *scores, const int64_t 
         std::push_heap(heap.begin(), heap.end(), worse);
       }
     }
-  }
-  std::sort(heap.begin(), heap.end(), worse);
-  for (size_t k = 0; k < heap.size(); k++)
+  };
+  // large shards are cut over a few host threads; every piece keeps its own top `keep`
+  struct Piece { int shard; int64_t lo, hi; };
+  std::vector<Piece> pieces;
+  const int64_t grain = 1 << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  const int64_t maxpar = std::max<int64_t>(1, std::min<int64_t>(hw ? hw : 1, 8));
+  for (int s = 0; s < nshards; s++)
   {
-    out_seqno[k] = heap[k].seqno;
-    out_score[k] = heap[k].score;
+    const int64_t parts = std::max<int64_t>(1, std::min<int64_t>(maxpar, n[s] / grain));
+    for (int64_t k = 0; k < parts; k++) pieces.push_back(Piece{s, n[s] * k / parts, n[s] * (k + 1) / parts});
+  }
+  std::vector<Part> parts(pieces.size());
+  if (pieces.size() <= 1)
+  {
+    for (size_t k = 0; k < pieces.size(); k++)
+      scan(parts[k], scores[pieces[k].shard], pieces[k].lo, pieces[k].hi, seqno_base[pieces[k].shard]);
+  }
+  else
+  {
+    std::vector<std::thread> pool;
+    std::atomic<size_t> next(0);
+    const size_t nthreads = std::min<size_t>(pieces.size(), (size_t)maxpar);
+    for (size_t t = 0; t < nthreads; t++)
+      pool.emplace_back([&]() {
+        for (size_t k = next++; k < pieces.size(); k = next++)
+          scan(parts[k], scores[pieces[k].shard], pieces[k].lo, pieces[k].hi, seqno_base[pieces[k].shard]);
+      });
+    for (std::thread &t : pool) t.join();
+  }
+  std::vector<Hit> all;
+  int64_t tot = 0, obv = 0;
+  for (Part &P : parts)
+  {
+    all.insert(all.end(), P.heap.begin(), P.heap.end());
+    tot += P.tot;
+    obv += P.obv;
+  }
+  std::sort(all.begin(), all.end(), worse);
+  if ((int64_t)all.size() > keep) all.resize((size_t)keep);
+  for (size_t k = 0; k < all.size(); k++)
+  {
+    out_seqno[k] = all[k].seqno;
+    out_score[k] = all[k].score;
   }
   if (totalhits) *totalhits = tot;
   if (obvious) *obvious = obv;
-  return (int64_t)heap.size();
+  return (int64_t)all.size();
 }
 
 int swb_set_mode(swb_db *db, int mode)
