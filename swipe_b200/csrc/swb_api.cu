@@ -809,9 +809,9 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
   const long long *cut_off = S.translate ? S.nt_offsets.data() : offsets;
   std::vector<long long> cut;                       // chunk c covers source sequences [cut[c], cut[c+1])
   cut.push_back(0);
-  // the first chunks are small so that the scan can start while most of the shard is still on the
-  // wire (32, 64, 128 MB, then full size)
-  const bool ramp = getenv("SWB_CHUNK_BYTES") == nullptr;
+  // asynchronous open: the first chunks are small so that the scan can start while most of the shard
+  // is still on the wire (32, 64, 128 MB, then full size)
+  const bool ramp = !wait && getenv("SWB_CHUNK_BYTES") == nullptr;   // only an asynchronous open overlaps
   while (cut.back() < nsrc)
   {
     const long long lo = cut.back();
@@ -1223,13 +1223,18 @@ int64_t swb_topk_merge(int nshards, const int64_t *const *scores, const int64_t 
   };
   struct Part { std::vector<Hit> heap; int64_t tot = 0, obv = 0; };
   auto scan = [&](Part &P, const int64_t *sc, int64_t lo, int64_t hi, int64_t base) {
-    std::vector<Hit> &heap = P.heap;                 // min-heap on (score, seqno) of the best so far
-    for (int64_t i = lo; i < hi; i++)
+    std::vector<Hit> heap;                           // min-heap on (score, seqno) of the best so far
+    heap.reserve((size_t)std::min<int64_t>(keep, hi - lo) + 1);
+    int64_t tot = 0, obv = 0;
+    int64_t cut = min_score;                         // scores below cannot enter (raised once the heap is full)
+    // highest sequence number first: among equal scores the higher number wins (hits.cc:188-191), so
+    // in this order a tie never displaces an entry and the heap only changes on a better score
+    for (int64_t i = hi - 1; i >= lo; i--)
     {
       const int64_t v = sc[i];
-      if (v > upper_score) P.obv++;
-      if (v >= min_score) P.tot++;
-      if (v < min_score || v > upper_score || keep == 0) continue;
+      tot += v >= min_score;
+      obv += v > upper_score;
+      if (v < cut || v > upper_score || keep == 0) continue;
       const Hit h = {v, base + i};
       if ((int64_t)heap.size() < keep)
       {
@@ -1242,7 +1247,11 @@ int64_t swb_topk_merge(int nshards, const int64_t *const *scores, const int64_t 
         heap.back() = h;
         std::push_heap(heap.begin(), heap.end(), worse);
       }
+      if ((int64_t)heap.size() == keep) cut = std::max(cut, heap.front().score);
     }
+    P.heap.swap(heap);
+    P.tot = tot;
+    P.obv = obv;
   };
   // large shards are cut over a few host threads; every piece keeps its own top `keep`
   struct Piece { int shard; int64_t lo, hi; };
