@@ -200,7 +200,10 @@ __host__ __device__ inline size_t swb_scan_smem(int G, int nq)
 // straight-line region for the instruction scheduler.  MP = the query needs more than one pass
 // (compiled out otherwise).  All shared-memory traffic goes through word/quad-word indices of
 // one typed array, so the compiler addresses it with 32-bit shared offsets.
-template <int G, int R, int MODE, bool MP>
+// KQ / KR != 0: gap penalties compiled in as immediates (both lanes, the mode's encoding) -- the DPX and
+// fp16 ops then read one register less each, which is worth ~4 % of the inner loop
+// (profiles/r1_ubench_tile_v2.txt, "immediate penalties"); 0 / 0 = read them from ScanParams.
+template <int G, int R, int MODE, bool MP, u32 KQ = 0, u32 KR = 0>
 __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const ScanParams P)
 {
   extern __shared__ uint4 smem4[];
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   const long long bnd0 = S.bnd_base + b0;
   const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);   // every warp holds all 8 streams
   const int nsteps = nblk_max > 0 ? nblk_max + G - 1 : 0;
-  const u32 negq = P.negq, negr = P.negr;
+  const u32 negq = (KQ | KR) ? KQ : P.negq, negr = (KQ | KR) ? KR : P.negr;
   const bool first_quarter = (lane >> 3) == 0;
   const bool last_quarter = (lane >> 3) == 3 && g < G - 1;
   const int brow = g >> 2;                             // first table row this thread builds

@@ -324,13 +324,22 @@ int prepare_tables(Tables &t, const unsigned char *query, long long qlen, const 
 
 // ---- kernel shapes -----------------------------------------------------------------------------
 typedef void (*scan_fn)(const ScanParams);
-struct ShapeEntry { int G, R, mode; scan_fn fn, fn_mp; };     // single-pass / multi-pass builds
+struct ShapeEntry { int G, R, mode; scan_fn fn, fn_mp; u32 kq, kr; };   // single-pass / multi-pass builds
+
+// hybrid-mode encodings of the two default scoring systems' penalties, compiled in as immediates:
+// BLOSUM62 11+1k (open+extend 12, extend 1) and nucleotide 5+2k (7, 2)
+#define SWB_KQ(q) (0x8000u | (q)) | ((0x8000u | (q)) << 16)
+#define SWB_KR(r) ((0x10000u - (r)) | ((0x10000u - (r)) << 16))
 
 #define SWB_SHAPE(G, R)                                                                          \
   {G, R, SWB_MODE_INT16, swb_scan_kernel<G, R, SWB_MODE_INT16, false>,                           \
-   swb_scan_kernel<G, R, SWB_MODE_INT16, true>},                                                 \
+   swb_scan_kernel<G, R, SWB_MODE_INT16, true>, 0, 0},                                           \
   {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID, false>,                         \
-   swb_scan_kernel<G, R, SWB_MODE_HYBRID, true>}
+   swb_scan_kernel<G, R, SWB_MODE_HYBRID, true>, 0, 0},                                          \
+  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID, false, SWB_KQ(12), SWB_KR(1)>,  \
+   swb_scan_kernel<G, R, SWB_MODE_HYBRID, true, SWB_KQ(12), SWB_KR(1)>, SWB_KQ(12), SWB_KR(1)},  \
+  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID, false, SWB_KQ(7), SWB_KR(2)>,   \
+   swb_scan_kernel<G, R, SWB_MODE_HYBRID, true, SWB_KQ(7), SWB_KR(2)>, SWB_KQ(7), SWB_KR(2)}
 
 const ShapeEntry g_shapes[] = {
     SWB_SHAPE(8, 8),   SWB_SHAPE(8, 13),  SWB_SHAPE(8, 16),  SWB_SHAPE(16, 12), SWB_SHAPE(16, 16),
@@ -340,18 +349,23 @@ const ShapeEntry g_shapes[] = {
 const int g_nshapes = (int)(sizeof(g_shapes) / sizeof(g_shapes[0]));
 
 // rows covered per pass = G*R; cost ~ padded rows * (1 + per-step overhead / R)
-const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, int *npass)
+// (kq, kr): the penalties in the mode's packed encoding; a build with exactly these compiled in is
+// preferred over the generic one of the same shape
+const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, u32 kq, u32 kr, int *npass)
 {
   const ShapeEntry *best = nullptr;
   double best_cost = 0;
+  const bool allow_spec = getenv("SWB_NO_SPEC") == nullptr;
   for (int i = 0; i < g_nshapes; i++)
   {
     const ShapeEntry &s = g_shapes[i];
     if (s.mode != mode) continue;
+    const bool spec = (s.kq | s.kr) != 0;
+    if (spec && !(allow_spec && s.kq == kq && s.kr == kr)) continue;
     if (db->force_G && (s.G != db->force_G || s.R != db->force_R)) continue;
     const long long rows = (long long)s.G * s.R;
     const long long np = std::max<long long>(1, (qlen + rows - 1) / rows);
-    const double cost = (double)(np * rows) * (1.0 + 2.5 / s.R) * (np > 1 ? 1.02 : 1.0);
+    const double cost = (double)(np * rows) * (1.0 + 2.5 / s.R) * (np > 1 ? 1.02 : 1.0) * (spec ? 0.97 : 1.0);
     if (!best || cost < best_cost) { best = &s; best_cost = cost; *npass = (int)np; }
   }
   return best;
@@ -445,7 +459,14 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     SWB_TRY(prepare_tables(probe, query, qlen, sc, mode, 0));
     if (mode != SWB_MODE_INT16 && !probe.hybrid_ok) mode = SWB_MODE_INT16;
   }
-  const ShapeEntry *shape = choose_shape(db, qlen, mode, &npass);
+  u32 kq = 0, kr = 0;
+  if (mode == SWB_MODE_HYBRID && sc->gap_open_extend <= 1023 && sc->gap_extend >= 1 && sc->gap_extend <= 1023)
+  {
+    const u32 a = (u32)(unsigned short)enc16(-sc->gap_open_extend, mode), b = (u32)(unsigned short)(short)(-sc->gap_extend);
+    kq = a | (a << 16);
+    kr = b | (b << 16);
+  }
+  const ShapeEntry *shape = choose_shape(db, qlen, mode, kq, kr, &npass);
   if (!shape) return SWB_ERR_INTERNAL;
   const long long rows_padded = (long long)npass * shape->G * shape->R;
   SWB_TRY(prepare_tables(tb, query, qlen, sc, mode, (int)rows_padded));

@@ -1,10 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log | cut -c1-300
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench.json'))
-print(d['value'], d['ms_per_step'], d['e2e'], d['gpu_launches'], d['roofline']['traffic'])
-PY
+for v in "SWB_NO_SPEC=1" "SWB_X=1" "SWB_NO_SPEC=1" "SWB_X=1"; do
+  echo "== $v"; env $v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['kernel_ms'], d['gpu_launches'])"
+done
