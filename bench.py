@@ -335,6 +335,10 @@ def main():
                     "peak_cells_per_clk_per_sm_ubench_int16": 25.6,
                     "peak_cells_per_clk_per_sm_ubench_hybrid": 29.9,
                     "frac_of_ubench_hybrid": cells_per_clk_sm / 29.9,
+                    # 3.5 DPX ops per cell pair at one warp instruction per 2 clk on the 16-lane ALU
+                    # pipe = 7 clk per 64 cells per SM sub-partition
+                    "alu_pipe_bound_cells_per_clk_per_sm": 4 * 64 / 7.0,
+                    "frac_of_alu_pipe_bound": cells_per_clk_sm / (4 * 64 / 7.0),
                     "nominal_8bit_tcups": 8.27,
                     "frac_of_nominal_8bit": cells / (scan_avg * 1e-3) * 1e-12 / 8.27},
             "counters": {k: counters[k] for k in ("ref_width7", "ref_width16", "ref_width63",

@@ -281,4 +281,36 @@ long ref_align(const unsigned char *q, long qlen, const unsigned char *d, long d
   return n;
 }
 
+// Statistics (stats.cc, NCBI's blastkar tables) and the query-side codon table (query.cc:366-444),
+// for pinning swb_stats_* and swb_translate_table.
+long ref_stats_params(const char *matrix, long go, long ge, double *p)
+{
+  return stats_getparams(matrix, go, ge, p, p + 1, p + 2, p + 3, p + 4);
+}
+
+long ref_stats_params_nt(long match, long mismatch, long go, long ge, double *p)
+{
+  return stats_getparams_nt(match, mismatch, go, ge, p, p + 1, p + 2, p + 3, p + 4);
+}
+
+long ref_stats_prefs(const char *matrix, long *go, long *ge) { return stats_getprefs(matrix, go, ge); }
+
+extern "C++" int BlastComputeLengthAdjustment(double K, double logK, double alpha_d_lambda, double beta,
+                                              int query_length, long db_length, int db_num_seqs,
+                                              int *length_adjustment);
+
+long ref_length_adjustment(double K, double logK, double a_d_l, double beta, long qlen, long dblen, long nseq)
+{
+  int adj = 0;
+  BlastComputeLengthAdjustment(K, logK, a_d_l, beta, (int)qlen, dblen, (int)nseq, &adj);
+  return adj;
+}
+
+extern char q_translate[];
+void ref_translate_table(long gencode, unsigned char *out)
+{
+  translate_init(gencode, gencode);
+  memcpy(out, q_translate, 4096);
+}
+
 }  // extern "C"
