@@ -349,12 +349,23 @@ const ShapeEntry g_shapes[] = {
 const int g_nshapes = (int)(sizeof(g_shapes) / sizeof(g_shapes[0]));
 
 // rows covered per pass = G*R; cost ~ padded rows * (1 + per-step overhead / R)
+// Measured throughput of every compiled shape on padded rows (TCUPS of the hybrid build with the
+// penalties compiled in, 2 M-subject shard, tools/tune_shapes.py -> profiles/r1_tune_shapes.txt):
+// single pass / multi-pass.  Shapes without a multi-pass measurement use 0.93 x single pass.
+struct ShapeEff { int G, R; double sp, mp; };
+const ShapeEff g_eff[] = {
+    {8, 8, 5.0, 0},     {8, 13, 5.52, 0},    {8, 16, 6.00, 0},    {16, 12, 6.42, 0},   {16, 16, 7.04, 0},
+    {16, 20, 7.09, 0},  {16, 24, 7.19, 6.18}, {32, 12, 6.36, 5.71}, {32, 16, 6.64, 6.44}, {32, 20, 6.80, 6.74},
+    {32, 24, 7.50, 6.45}, {32, 28, 7.39, 6.41}, {32, 32, 6.62, 6.38},
+};
+
 // (kq, kr): the penalties in the mode's packed encoding; a build with exactly these compiled in is
-// preferred over the generic one of the same shape
+// preferred over the generic one of the same shape (except where it measured slower).  The shape
+// that scores the query's rows fastest wins: efficiency x qlen / (passes x G x R).
 const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, u32 kq, u32 kr, int *npass)
 {
   const ShapeEntry *best = nullptr;
-  double best_cost = 0;
+  double best_rate = 0;
   const bool allow_spec = getenv("SWB_NO_SPEC") == nullptr;
   for (int i = 0; i < g_nshapes; i++)
   {
@@ -365,8 +376,14 @@ const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, u32 k
     if (db->force_G && (s.G != db->force_G || s.R != db->force_R)) continue;
     const long long rows = (long long)s.G * s.R;
     const long long np = std::max<long long>(1, (qlen + rows - 1) / rows);
-    const double cost = (double)(np * rows) * (1.0 + 2.5 / s.R) * (np > 1 ? 1.02 : 1.0) * (spec ? 0.97 : 1.0);
-    if (!best || cost < best_cost) { best = &s; best_cost = cost; *npass = (int)np; }
+    double eff = 5.0;
+    for (const ShapeEff &e : g_eff)
+      if (e.G == s.G && e.R == s.R) eff = np > 1 ? (e.mp > 0 ? e.mp : 0.93 * e.sp) : e.sp;
+    if (!spec) eff *= 0.955;                                   // generic builds read the penalties from registers
+    else if (s.G == 32 && s.R == 32 && np == 1) eff *= 0.87;   // this one spills with the immediates (5.60 vs 6.13)
+    if (mode == SWB_MODE_INT16) eff *= 0.84;
+    const double rate = eff * (double)std::max<long long>(qlen, 1) / (double)(np * rows);
+    if (!best || rate > best_rate) { best = &s; best_rate = rate; *npass = (int)np; }
   }
   return best;
 }

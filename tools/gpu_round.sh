@@ -3,12 +3,10 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()"
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err; echo "ref rc=$?"
 tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json gpurun_out/bench_reference.json
-for v in "SWB_MERGE=0" "SWB_OVERSUB=2" "SWB_OVERSUB=3"; do
-  echo "== $v"; env $v python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['kernel_ms'], d['gpu_launches'])"
-done
 timeout 900 python tools/sweep_configs.py 5000000 ${NDNA:-50000000} 2 > gpurun_out/sweep.jsonl 2> gpurun_out/sweep.err; echo "sweep rc=$?"; cat gpurun_out/sweep.jsonl; tail -2 gpurun_out/sweep.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
