@@ -132,6 +132,27 @@ def run_reference_cpu(q, residues, offsets, budget_s, threads):
         n, int(offsets[n]), t1 - t0)
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: keep this rank's host threads and its pinned buffers on the NUMA node the GPU
+    hangs off, so that eight simultaneous uploads do not cross sockets.  Best effort."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -182,6 +203,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the scan has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     q, residues, offsets = make_workload(args.nseq, args.qlen, rank)

@@ -40,7 +40,7 @@ def test_product_has_no_cpu_fallback():
 def test_product_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "swipe_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".cpp", ".inc", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in text and "liborc" not in text and "libswipe_ref" not in text, f
 
