@@ -136,6 +136,8 @@ int swb_blastdb_close(swb_blastdb *b);
 const char *swb_blastdb_error(void);   /* text of the last open failure on this thread */
 int swb_blastdb_info(const swb_blastdb *b, int64_t *nseq, int64_t *symbols, int64_t *longest,
                      int *volumes);
+/* membership bit and the masked totals of an alias database (database.cc:1046-1065) */
+int swb_blastdb_masked_info(const swb_blastdb *b, int64_t *memb_bit, int64_t *nseq, int64_t *symbols);
 const char *swb_blastdb_title(const swb_blastdb *b);
 const char *swb_blastdb_date(const swb_blastdb *b);
 /* length in residues / nucleotides (database.cc:1246-1261), or a negative status */
@@ -238,9 +240,11 @@ const char *swb_gencode_name(int gencode);
 int64_t swb_translate(const uint8_t *nt, int64_t len, int strand, int frame, const uint8_t *table,
                       uint8_t *out);                               /* query.cc:450-506 */
 /* The deflines of a .phr/.nhr record as text, one per line (asnparse.cc:753-887); returns their
- * count, *needed = bytes required (SWB_ERR_RANGE when cap is too small).                         */
+ * count, *needed = bytes required (SWB_ERR_RANGE when cap is too small).  memb / taxids filter the
+ * deflines like the reference's -x list and alias MEMB_BIT do (database.cc:718-733, :1457-1481).  */
 int64_t swb_defline_text(const uint8_t *data, int64_t len, int show_gis, int show_taxid, int64_t memb,
-                         char *buf, int64_t cap, int64_t *needed);
+                         const uint8_t *taxids, int64_t taxid_bytes, char *buf, int64_t cap,
+                         int64_t *needed);
 
 /* ---- alignment of a hit (host) -------------------------------------------------------------
  * swb_align: the reference's align() (align.cc:469-519) as hits_align calls it for the best -b hits

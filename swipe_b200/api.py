@@ -14,17 +14,17 @@ STATUS = {0: "SWB_OK", -1: "SWB_ERR_ARG", -2: "SWB_ERR_NO_DEVICE", -3: "SWB_ERR_
 # every symbol include/swipe_b200.h declares (tests check the library exports all of them)
 EXPORTS = ["swb_abi_version", "swb_align", "swb_blastdb_close", "swb_blastdb_date",
            "swb_blastdb_error", "swb_blastdb_header", "swb_blastdb_included", "swb_blastdb_info",
-           "swb_blastdb_open", "swb_blastdb_seqlen", "swb_blastdb_sequence", "swb_blastdb_title",
-           "swb_db_close", "swb_db_info", "swb_db_open", "swb_db_open_async",
-           "swb_db_open_blast", "swb_db_open_blast_translated", "swb_db_open_ms", "swb_db_wait",
-           "swb_defline_text", "swb_device_count", "swb_gencode_name", "swb_host_alloc",
-           "swb_host_free", "swb_last_cuda_error", "swb_matrix_builtin", "swb_matrix_limits",
-           "swb_matrix_nucleotide", "swb_matrix_parse", "swb_matrix_read", "swb_query_parse",
-           "swb_revcomp", "swb_search", "swb_search_end", "swb_search_list",
-           "swb_set_mode", "swb_set_shape", "swb_stats_bits", "swb_stats_default_gaps",
-           "swb_stats_evalue", "swb_stats_init", "swb_stats_length_adjustment", "swb_stats_params",
-           "swb_stats_params_nt", "swb_strerror", "swb_topk_merge", "swb_translate",
-           "swb_translate_table", "swb_trim"]
+           "swb_blastdb_masked_info", "swb_blastdb_open", "swb_blastdb_seqlen", "swb_blastdb_sequence",
+           "swb_blastdb_title", "swb_db_close", "swb_db_info", "swb_db_open",
+           "swb_db_open_async", "swb_db_open_blast", "swb_db_open_blast_translated", "swb_db_open_ms",
+           "swb_db_wait", "swb_defline_text", "swb_device_count", "swb_gencode_name",
+           "swb_host_alloc", "swb_host_free", "swb_last_cuda_error", "swb_matrix_builtin",
+           "swb_matrix_limits", "swb_matrix_nucleotide", "swb_matrix_parse", "swb_matrix_read",
+           "swb_query_parse", "swb_revcomp", "swb_search", "swb_search_end",
+           "swb_search_list", "swb_set_mode", "swb_set_shape", "swb_stats_bits",
+           "swb_stats_default_gaps", "swb_stats_evalue", "swb_stats_init", "swb_stats_length_adjustment",
+           "swb_stats_params", "swb_stats_params_nt", "swb_strerror", "swb_topk_merge",
+           "swb_translate", "swb_translate_table", "swb_trim"]
 
 
 class SwbError(RuntimeError):

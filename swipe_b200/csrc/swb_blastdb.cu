@@ -207,6 +207,8 @@ int swb_blastdb_open(const char *basename, int nucleotide, swb_blastdb **out)
     if (mask_from)
     {
       v.masked_maxoid = mask_from->maxoid;
+      v.masked_nseq = mask_from->nseq;
+      v.masked_length = mask_from->length;
       if (!map_file(path + mskfile, &v.msk, &v.len_msk, err)) return false;
     }
     return true;
@@ -217,7 +219,7 @@ int swb_blastdb_open(const char *basename, int nucleotide, swb_blastdb **out)
   {
     // one level of nesting, as the reference handles (database.cc:790-880)
     b->title = top.title;
-    b->memb_bit = top.memb_bit != 0;
+    b->memb_bit = top.memb_bit;
     for (size_t i = 0; i < top.dblist.size(); i++)
     {
       const std::string base2 = path + top.dblist[i];
@@ -237,7 +239,7 @@ int swb_blastdb_open(const char *basename, int nucleotide, swb_blastdb **out)
       }
       else
       {
-        if (top.oidlist.empty()) b->memb_bit = false;
+        if (top.oidlist.empty()) b->memb_bit = 0;
         if (b->memb_bit && (top.oidlist.size() != 1 || top.dblist.size() != 1))
         {
           err = "Illegal alias file (1).";
@@ -264,6 +266,8 @@ int swb_blastdb_open(const char *basename, int nucleotide, swb_blastdb **out)
     v.first = first;
     first += v.nseq;
     b->symcount += v.symcount;
+    b->masked_nseq += v.masked_nseq;
+    b->masked_symcount += v.masked_length;
     if (v.longest > b->longest) b->longest = v.longest;
   }
   b->nseq = first;
@@ -294,6 +298,17 @@ int swb_blastdb_info(const swb_blastdb *b, int64_t *nseq, int64_t *symbols, int6
   if (symbols) *symbols = b->symcount;
   if (longest) *longest = b->longest;
   if (volumes) *volumes = (int)b->vols.size();
+  return SWB_OK;
+}
+
+// totals hits_init uses for a masked database (db_getseqcount_masked / db_getsymcount_masked,
+// database.cc:1046-1065): the alias file's NSEQ / LENGTH; equal to the plain totals when not masked
+int swb_blastdb_masked_info(const swb_blastdb *b, int64_t *memb_bit, int64_t *nseq, int64_t *symbols)
+{
+  if (!b) return SWB_ERR_ARG;
+  if (memb_bit) *memb_bit = b->memb_bit;
+  if (nseq) *nseq = b->memb_bit ? b->masked_nseq : b->nseq;
+  if (symbols) *symbols = b->memb_bit ? b->masked_symcount : b->symcount;
   return SWB_OK;
 }
 

@@ -13,7 +13,7 @@ struct SwbVolume
   long long nseq = 0, symcount = 0, longest = 0;
   std::string title, date;
   const uint8_t *tab_hdr = nullptr, *tab_seq = nullptr, *tab_amb = nullptr;        // BE u32 [nseq+1]
-  long long masked_maxoid = 0;
+  long long masked_maxoid = 0, masked_nseq = 0, masked_length = 0;   // from the alias file (NSEQ / LENGTH)
   long long first = 0;                  // global number of the volume's first sequence
 
   static inline uint32_t be32(const uint8_t *p)
@@ -28,7 +28,8 @@ struct SwbVolume
 struct swb_blastdb
 {
   bool nucleotide = false;
-  bool memb_bit = false;
+  long long memb_bit = 0;              // MEMB_BIT of the alias file; 0 = not masked
+  long long masked_nseq = 0, masked_symcount = 0;
   std::vector<SwbVolume> vols;
   long long nseq = 0, symcount = 0, longest = 0;
   std::string title, date, error;

@@ -406,9 +406,12 @@ int64_t swb_translate(const uint8_t *nt, int64_t len, int strand, int frame, con
 
 // The deflines of one sequence header as text, one per line ('\n' separated), each
 // "<seqids joined by |>[|taxid|N][|link|N][|memb|N] <title>" (asnparse.cc:753-887).  memb != 0
-// keeps only deflines whose membership bits include it.  Returns the number of deflines.
+// keeps only deflines whose membership bits include it.  Returns the number of deflines kept.
+// taxids != NULL: a bitmap (bit t & 7 of byte t / 8, db_check_taxid database.cc:718-733); deflines
+// whose taxid is not in it are dropped, like deflines failing the membership test.
 int64_t swb_defline_text(const uint8_t *data, int64_t len, int show_gis, int show_taxid, int64_t memb,
-                         char *buf, int64_t cap, int64_t *needed)
+                         const uint8_t *taxids, int64_t taxid_bytes, char *buf, int64_t cap,
+                         int64_t *needed)
 {
   if (!data || len < 0 || cap < 0 || (cap > 0 && !buf)) return SWB_ERR_ARG;
   Ber top{data, data + len};
@@ -441,6 +444,7 @@ int64_t swb_defline_text(const uint8_t *data, int64_t len, int show_gis, int sho
           ber_within(d, 0xa4, [&](Ber &v) { ber_within(v, 0x30, [&](Ber &s) { while (more(s)) links = ber_uint(s); }); });
         while (more(d)) ber_skip(d);
         if (((long long)membership & memb) != memb) return;
+        if (taxids && !((long long)(taxid >> 3) < taxid_bytes && ((taxids[taxid >> 3] >> (taxid & 7)) & 1))) return;
         std::string line = ids;
         char num[64];
         if (show_taxid)

@@ -10,7 +10,7 @@
 //   align_chunk / hits_align .............. swipe.cc:339-414, hits.cc:546-623 (swb_search_end + swb_align)
 //   hits_show_plain / _xml / _tsv ......... hits.cc:647-1176, :1660-1945
 //   show_deflines ......................... asnparse.cc:889-971
-// Not carried over: -x taxid lists, -N dump, -m 99, symtype 5, MPI.  `-a` (threads in the
+// Not carried over: -m 99, symtype 5 ("sound"), MPI.  `-a` (threads in the
 // reference) selects how many GPUs share the database, one host thread each.
 #include "../../include/swipe_b200.h"
 
@@ -64,8 +64,8 @@ struct Options
   long symtype = 1, show_gis = 0, show_taxid = 0;
   double expect = 10.0, minexpect = 0.0;
   long matchscore = 1, mismatchscore = -3, querystrands = 3, query_gencode = 1, db_gencode = 1;
-  long effdbsize = 0;
-  const char *outfile = nullptr;
+  long effdbsize = 0, dump = 0;
+  const char *outfile = nullptr, *taxidfile = nullptr;
 };
 
 const char SYM_AA[] = "-ABCDEFGHIKLMNPQRSTVWXYZU*OJ####";
@@ -95,6 +95,8 @@ void usage(const char *prog)
   fprintf(out, "  -S, --strand=NAME/NUM      query strands to search [1-3] (3)\n");
   fprintf(out, "  -Q, --query_gencode=NUM    query genetic code [1-23] (1)\n");
   fprintf(out, "  -D, --db_gencode=NUM       database genetic code [1-23] (1)\n");
+  fprintf(out, "  -x, --taxidlist=FILE       taxid list filename (none)\n");
+  fprintf(out, "  -N, --dump=NUM             dump database [0-2=no,yes,split headers] (0)\n");
   fprintf(out, "  -H, --show_taxid           show taxid etc in results (no)\n");
   fprintf(out, "  -o, --out=FILE             output file (stdout)\n");
   fprintf(out, "  -z, --dbsize=NUM           set effective database size (0)\n");
@@ -152,7 +154,7 @@ Options parse_args(int argc, char **argv)
       case 'K': break;
       case 'm': o.view = atol(optarg); break;
       case 'M': o.matrixname = optarg; break;
-      case 'N': fatal("Database dumps (-N) are not supported by this front end.");
+      case 'N': o.dump = atol(optarg); break;
       case 'o': o.outfile = optarg; break;
       case 'p':
         if (!strcmp(optarg, "blastn")) o.symtype = 0;
@@ -173,7 +175,7 @@ Options parse_args(int argc, char **argv)
         break;
       case 'u': o.maxscore = atol(optarg); break;
       case 'v': o.maxmatches = atol(optarg); break;
-      case 'x': fatal("Taxid lists (-x) are not supported by this front end.");
+      case 'x': o.taxidfile = optarg; break;
       case 'z': o.effdbsize = atol(optarg); break;
       default:
         usage(argv[0]);
@@ -217,6 +219,7 @@ Options parse_args(int argc, char **argv)
     fatal("Illegal query genetic code specified.");
   if (o.db_gencode < 1 || o.db_gencode > 23 || !swb_gencode_name((int)o.db_gencode))
     fatal("Illegal database genetic code specified.");
+  if (o.dump < 0 || o.dump > 2) fatal("Illegal dump mode.");
   return o;
 }
 
@@ -263,6 +266,8 @@ struct Run
   Options o;
   swb_blastdb *bdb = nullptr;
   int64_t nseq = 0, symcount = 0, longest = 0;
+  int64_t memb_bit = 0, masked_nseq = 0, masked_symcount = 0;   // alias-file mask (database.cc:1046-1065)
+  std::vector<uint8_t> taxids;          // -x: bitmap of the taxids to keep (database.cc:735-772)
   bool db_nt = false, translated_db = false;
   int64_t matrix[1024];
   uint8_t qtable[4096], dtable[4096];
@@ -290,6 +295,21 @@ void merge_hits(Run &R, std::vector<Hit> &local)
   }
 }
 
+// db_check_inclusion (database.cc:1465-1481): the membership bit of a masked database, then the
+// -x list: a sequence stays when at least one of its deflines passes both filters
+bool included(const Run &R, int64_t seqno)
+{
+  if (!swb_blastdb_included(R.bdb, seqno)) return false;
+  if (R.taxids.empty()) return true;
+  const uint8_t *hp = nullptr;
+  int64_t hl = 0;
+  if (swb_blastdb_header(R.bdb, seqno, &hp, &hl) != SWB_OK) return false;
+  char tmp[1];
+  int64_t need = 0;
+  const int64_t n = swb_defline_text(hp, hl, 0, 0, R.memb_bit, R.taxids.data(), (int64_t)R.taxids.size(), tmp, 0, &need);
+  return n > 0 || (n == SWB_ERR_RANGE && need > 1);
+}
+
 // one GPU's share of search_chunk: every query strand / frame against every subject of the shard
 void search_shard(Run &R, const Query &q, Shard &S)
 {
@@ -313,7 +333,7 @@ void search_shard(Run &R, const Query &q, Shard &S)
         const int64_t s = scores[(size_t)j];
         if (s < threshold || s > R.st.upper_threshold) continue;
         const int64_t seqno = S.first + j / unit;
-        if (!swb_blastdb_included(R.bdb, seqno)) continue;
+        if (!included(R, seqno)) continue;
         Hit h;
         h.seqno = seqno;
         h.score = s;
@@ -433,13 +453,16 @@ void show_header(const Run &R, const Hit &h, long show_gis, long indent, size_t 
 {
   int64_t need = 0;
   std::vector<char> buf(h.header.size() * 4 + 4096);
+  const uint8_t *tx = R.taxids.empty() ? nullptr : R.taxids.data();
   int64_t n = swb_defline_text((const uint8_t *)h.header.data(), (int64_t)h.header.size(), (int)show_gis,
-                               (int)R.o.show_taxid, 0, buf.data(), (int64_t)buf.size(), &need);
+                               (int)R.o.show_taxid, R.memb_bit, tx, (int64_t)R.taxids.size(), buf.data(),
+                               (int64_t)buf.size(), &need);
   if (n == SWB_ERR_RANGE)
   {
     buf.resize((size_t)need + 1);
     n = swb_defline_text((const uint8_t *)h.header.data(), (int64_t)h.header.size(), (int)show_gis,
-                         (int)R.o.show_taxid, 0, buf.data(), (int64_t)buf.size(), &need);
+                         (int)R.o.show_taxid, R.memb_bit, tx, (int64_t)R.taxids.size(), buf.data(),
+                         (int64_t)buf.size(), &need);
   }
   if (n < 0) fatal("Error parsing binary ASN.1 in database sequence definition.");
   std::vector<std::string> lines;
@@ -753,7 +776,7 @@ void show_run_header(const Run &R, const Query &q)
   fprintf(out, "Database file:     %s\n", o.databasename.c_str());
   fprintf(out, "Database title:    %s\n", swb_blastdb_title(R.bdb));
   fprintf(out, "Database time:     %s\n", swb_blastdb_date(R.bdb));
-  fprintf(out, "Database size:     %ld residues in %ld sequences\n", (long)R.symcount, (long)R.nseq);
+  fprintf(out, "Database size:     %ld residues in %ld sequences\n", (long)R.masked_symcount, (long)R.masked_nseq);
   fprintf(out, "Longest db seq:    %ld residues\n", (long)R.longest);
   if (o.effdbsize > 0) fprintf(out, "Effecive db size:  %ld\n", o.effdbsize);
   fprintf(out, "Query file name:   %s\n", o.queryname.c_str());
@@ -782,6 +805,7 @@ void show_run_header(const Run &R, const Query &q)
     fprintf(out, "Query genetic code:%s (%ld)\n", swb_gencode_name((int)o.query_gencode), o.query_gencode);
   if (o.symtype == 3 || o.symtype == 4)
     fprintf(out, "DB genetic code:   %s (%ld)\n", swb_gencode_name((int)o.db_gencode), o.db_gencode);
+  if (o.taxidfile) fprintf(out, "Taxid filename:    %s\n", o.taxidfile);
   fprintf(out, "\n");
 }
 
@@ -818,7 +842,7 @@ void work(Run &R, Query &q)
   if (o.view == 0) show_run_header(R, q);
   // hits_init (hits.cc:283-511)
   R.keephits = std::max(o.maxmatches, o.alignments);
-  int64_t maxhits = R.nseq;
+  int64_t maxhits = R.masked_nseq;
   if (o.symtype == 0) maxhits *= o.querystrands == 3 ? 2 : 1;
   else if (o.symtype == 2) maxhits *= o.querystrands == 3 ? 6 : 3;
   else if (o.symtype == 3) maxhits *= 6;
@@ -826,7 +850,7 @@ void work(Run &R, Query &q)
   R.keephits = std::min(R.keephits, maxhits);
   const int64_t qlen = (o.symtype == 0 || o.symtype == 2 || o.symtype == 4) ? (int64_t)q.nt[0].size() : (int64_t)q.aa[0].size();
   check(swb_stats_init((int)o.symtype, o.matrixname.c_str(), o.matchscore, o.mismatchscore, o.gapopen,
-                       o.gapextend, qlen, R.symcount, R.nseq, o.effdbsize, o.minscore, o.maxscore, o.expect,
+                       o.gapextend, qlen, R.masked_symcount, R.masked_nseq, o.effdbsize, o.minscore, o.maxscore, o.expect,
                        o.minexpect, &R.st), "statistics");
   if (!R.st.available && o.view == 0)
     fprintf(out, "Statistical parameters are not available for the scoring system specified.\nBit scores and E-values will not be computed.\n\n");
@@ -856,7 +880,7 @@ void work(Run &R, Query &q)
     gmtime_r(&w1, &tmv); strftime(b1, sizeof b1, "%a, %e %b %Y %T UTC", &tmv);
     gmtime_r(&w2, &tmv); strftime(b2, sizeof b2, "%a, %e %b %Y %T UTC", &tmv);
     const double elapsed = (double)(c2 - c1) / (double)sysconf(_SC_CLK_TCK);
-    double speed = (double)R.symcount;
+    double speed = (double)R.masked_symcount;
     if (o.symtype == 0) speed *= (double)q.nt[0].size() * (o.querystrands == 3 ? 2 : 1);
     else if (o.symtype == 1) speed *= (double)q.aa[0].size();
     else if (o.symtype == 2) speed *= (double)q.nt[0].size() * (o.querystrands == 3 ? 2 : 1);
@@ -888,6 +912,80 @@ int main(int argc, char **argv)
   check(swb_blastdb_open(o.databasename.c_str(), R.db_nt ? 1 : 0, &R.bdb), "database");
   int vols = 0;
   swb_blastdb_info(R.bdb, &R.nseq, &R.symcount, &R.longest, &vols);
+  swb_blastdb_masked_info(R.bdb, &R.memb_bit, &R.masked_nseq, &R.masked_symcount);
+  if (o.taxidfile)
+  {
+    FILE *f = fopen(o.taxidfile, "r");
+    if (!f) fatal("Unable to open taxid file %s.", o.taxidfile);
+    R.taxids.assign(64 * 1024, 0);
+    unsigned long t;
+    while (fscanf(f, "%lu\n", &t) > 0)
+    {
+      if (t / 8 >= R.taxids.size()) R.taxids.resize(t / 8 + 1, 0);
+      R.taxids[t / 8] |= (uint8_t)(1u << (t & 7));
+    }
+    fclose(f);
+  }
+  if (o.dump)
+  {
+    // db_show_fasta (database.cc:1483-1537) for every sequence; needs no GPU
+    const char *sym = R.db_nt ? "-ACMGRSVTWYHKDBN################" : SYM_AA;
+    std::vector<uint8_t> seq;
+    std::vector<char> buf(1 << 16);
+    for (int64_t s = 0; s < R.nseq; s++)
+    {
+      const uint8_t *hp = nullptr;
+      int64_t hl = 0, need = 0;
+      check(swb_blastdb_header(R.bdb, s, &hp, &hl), "reading a database header");
+      const uint8_t *tx = R.taxids.empty() ? nullptr : R.taxids.data();
+      int64_t n = swb_defline_text(hp, hl, 1, (int)o.show_taxid, R.memb_bit, tx, (int64_t)R.taxids.size(), buf.data(),
+                                   (int64_t)buf.size(), &need);
+      if (n == SWB_ERR_RANGE)
+      {
+        buf.resize((size_t)need + 1);
+        n = swb_defline_text(hp, hl, 1, (int)o.show_taxid, R.memb_bit, tx, (int64_t)R.taxids.size(), buf.data(),
+                             (int64_t)buf.size(), &need);
+      }
+      if (n < 0) fatal("Error parsing binary ASN.1 in database sequence definition.");
+      if (n == 0) continue;
+      const int64_t len = swb_blastdb_seqlen(R.bdb, s);
+      seq.resize((size_t)std::max<int64_t>(len, 1));
+      int64_t got = 0;
+      check(swb_blastdb_sequence(R.bdb, s, 0, seq.data(), len, &got), "reading a database sequence");
+      auto print_seq = [&]() {
+        for (int64_t i = 0; i < got; i += 80)
+        {
+          for (int64_t k = i; k < std::min<int64_t>(got, i + 80); k++) putc(sym[seq[(size_t)k] & 31], out);
+          fprintf(out, "\n");
+        }
+      };
+      const char *p = buf.data();
+      for (int64_t i = 0; i < n; i++)
+      {
+        const char *e = strchr(p, '\n');
+        std::string line = e ? std::string(p, e - p) : std::string(p);
+        p = e ? e + 1 : p + line.size();
+        if (o.dump == 2)
+        {
+          fprintf(out, ">%s\n", line.c_str());
+          print_seq();
+        }
+        else
+        {
+          if (i) fprintf(out, " ");
+          fprintf(out, ">%s", line.c_str());
+          if (i == n - 1)
+          {
+            fprintf(out, "\n");
+            print_seq();
+          }
+        }
+      }
+    }
+    swb_blastdb_close(R.bdb);
+    if (o.outfile) fclose(out);
+    return 0;
+  }
 
   if (o.symtype == 0) swb_matrix_nucleotide(o.matchscore, o.mismatchscore, R.matrix);
   else

@@ -17,6 +17,36 @@ def _defline(seq_id, title):
             bytes(12))
 
 
+def _int(v):
+    n = max(1, (int(v).bit_length() + 8) // 8)
+    return bytes([0x02, n]) + int(v).to_bytes(n, "big")
+
+
+def _wrap(tag, body):
+    return bytes([tag, 0x80]) + body + b"\0\0"
+
+
+def defline_set(deflines):
+    """deflines: list of dicts {title, lcl, gi, taxid, memb}: one Blast-def-line each (asnparse.cc:753-887)."""
+    out = b""
+    for d in deflines:
+        t = d["title"].encode()
+        body = _wrap(0xA0, bytes([0x1A, len(t)]) + t)
+        ids = b""
+        if d.get("gi") is not None:
+            ids += _wrap(0xAB, _int(d["gi"]))
+        if d.get("lcl") is not None:
+            i = d["lcl"].encode()
+            ids += _wrap(0xA0, _wrap(0xA1, bytes([0x1A, len(i)]) + i))
+        body += _wrap(0xA1, _wrap(0x30, ids))
+        if d.get("taxid"):
+            body += _wrap(0xA2, _int(d["taxid"]))
+        if d.get("memb"):
+            body += _wrap(0xA3, _wrap(0x30, _int(d["memb"])))
+        out += _wrap(0x30, body)
+    return _wrap(0x30, out)
+
+
 def _index(path, protein, title, date, nseq, residues, longest, tables):
     t = title.encode()
     d = date.encode()
@@ -31,13 +61,14 @@ def _index(path, protein, title, date, nseq, residues, longest, tables):
 
 
 def write_protein(basename, subjects, title="synthetic protein db", date="Oct 17, 2026  5:00 AM",
-                  ids=None):
-    """subjects: uint8 arrays of NCBIstdaa codes 1..27.  Writes basename.pin/.psq/.phr."""
+                  ids=None, headers=None):
+    """subjects: uint8 arrays of NCBIstdaa codes 1..27.  Writes basename.pin/.psq/.phr.
+    headers: optional list of defline_set() inputs, one per subject."""
     n = len(subjects)
     ids = ids or ["s%d" % i for i in range(n)]
     hdr, hoff = b"", [0]
     for i in range(n):
-        hdr += _defline(ids[i], "subject %d" % i)
+        hdr += defline_set(headers[i]) if headers else _defline(ids[i], "subject %d" % i)
         hoff.append(len(hdr))
     sq = bytearray(b"\0")
     soff = [1]

@@ -70,6 +70,24 @@ def build(tmp):
     tsubs.append(random_nt(rng, 2))
     tsubs.append(random_nt(rng, 4))
     blastdb.write_nucleotide(os.path.join(tmp, "t"), tsubs)
+    # deflines with gi numbers, taxids and membership bits; some sequences carry two deflines
+    nx = 45
+    headers = []
+    for i in range(nx):
+        tax = (9606, 10090, 562)[i % 3]
+        d = [{"title": "protein %d of organism %d" % (i, tax), "gi": 1000 + i, "lcl": "x%d" % i, "taxid": tax,
+              "memb": 1 if i % 4 == 0 else 0}]
+        if i % 5 == 0:
+            d.append({"title": "identical protein, other source", "gi": 5000 + i, "lcl": "y%d" % i,
+                      "taxid": 7227, "memb": 1 if i % 4 == 0 else 0})
+        headers.append(d)
+    blastdb.write_protein(os.path.join(tmp, "px"), subs[:nx], title="annotated db", headers=headers)
+    open(os.path.join(tmp, "tax.txt"), "w").write("10090\n7227\n")
+    keep = np.array([i % 4 == 0 for i in range(nx)])
+    open(os.path.join(tmp, "mx.msk"), "wb").write(b"\0\0\0\0" + np.packbits(keep).tobytes())
+    open(os.path.join(tmp, "pm.pal"), "w").write(
+        "TITLE masked subset\nDBLIST px\nOIDLIST mx.msk\nMEMB_BIT 1\nNSEQ %d\nLENGTH %d\nMAXOID %d\n" % (
+            int(keep.sum()), int(sum(len(subs[i]) for i in range(nx) if keep[i])), nx - 1))
     # a custom matrix without statistics
     m = fixtures.asym_matrix().reshape(32, 32)
     letters = scoring.SYM_AA[1:28]
@@ -92,6 +110,15 @@ CASES = {
     "protein_minscore_nolimit": "-d p -i q.fa -e 1e30 -c 30 -u 600 -m 7 -b 0 -v 1000",
     "protein_custom_matrix": "-d p -i q.fa -M asym.mat -G 7 -E 2 -v 12 -b 4",
     "protein_effdbsize": "-d p -i q.fa -z 5000000 -m 8 -b 10",
+    "annotated_plain": "-d px -i q.fa -e 1e30 -v 12 -b 3 -I -H",
+    "annotated_tsv": "-d px -i q.fa -e 1e30 -m 8 -b 45",
+    "taxid_list": "-d px -i q.fa -e 1e30 -x tax.txt -m 8 -b 45",
+    "taxid_list_plain": "-d px -i q.fa -e 1e30 -x tax.txt -v 30 -b 2 -H",
+    "masked_alias": "-d pm -i q.fa -e 1e30 -v 30 -b 2",
+    "masked_alias_tsv": "-d pm -i q.fa -m 8 -b 45",
+    "dump_protein": "-d px -N 1",
+    "dump_protein_split": "-d px -N 2",
+    "dump_nt": "-d n -p 0 -N 1",
     "nt_plain": "-d n -i qn.fa -p 0 -v 20 -b 10",
     "nt_tsv": "-d n -i qn.fa -p 0 -m 8 -b 60",
     "nt_plus_only": "-d n -i qn.fa -p 0 -S 1 -m 8 -b 30",

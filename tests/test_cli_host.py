@@ -48,3 +48,16 @@ def test_no_cpu_path(tmp_path):
     blastdb.write_fasta(str(tmp_path / "q.fa"), q)
     r = run(["-d", "p", "-i", "q.fa"], cwd=str(tmp_path))
     assert r.returncode == 1 and "no usable CUDA device" in r.stderr and r.stdout == ""
+
+
+def test_database_dump_matches_reference(tmp_path):
+    """-N 1 / -N 2 (db_show_fasta, database.cc:1483-1537) need no GPU: reader, defline parser and
+    nucleotide unpacking against the reference program's output for the same files."""
+    import os
+    import cli_cases
+    cli_cases.build(str(tmp_path))
+    gold = os.path.join(os.path.dirname(__file__), "golden", "cli_out")
+    for name in ("dump_protein", "dump_protein_split", "dump_nt"):
+        r = run(cli_cases.CASES[name].split(), cwd=str(tmp_path))
+        assert r.returncode == 0, r.stderr
+        assert cli_cases.normalise(r.stdout) == open(os.path.join(gold, name + ".txt")).read(), name

@@ -36,7 +36,8 @@ def lib():
     lib.swb_query_parse.restype = C.c_int64
     lib.swb_query_parse.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, P64, C.c_char_p, C.c_int64]
     lib.swb_defline_text.restype = C.c_int64
-    lib.swb_defline_text.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_char_p, C.c_int64, P64]
+    lib.swb_defline_text.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_char_p, C.c_int64, P64]
     lib.swb_gencode_name.restype = C.c_char_p
     return lib
 
@@ -147,10 +148,16 @@ def test_query_parsing(lib):
 
 
 def test_deflines(lib):
-    def text(data, gis=0, taxid=0, memb=0):
+    def text(data, gis=0, taxid=0, memb=0, keep=None):
         buf = C.create_string_buffer(4096)
         need = C.c_int64()
-        n = lib.swb_defline_text(data, len(data), gis, taxid, memb, buf, 4096, need)
+        bitmap = None
+        if keep is not None:
+            bitmap = np.zeros(2048, dtype=np.uint8)
+            for t in keep:
+                bitmap[t // 8] |= 1 << (t & 7)
+        n = lib.swb_defline_text(data, len(data), gis, taxid, memb, bitmap.ctypes.data if keep is not None else None,
+                                 2048 if keep is not None else 0, buf, 4096, need)
         return n, buf.value.decode()
     assert text(blastdb._defline("s22", "subject 22")) == (1, "lcl|s22 subject 22")
     # hand-encoded: title, seqids { gi 12345, ref { accession NP_000001, version 2 } }, taxid 9606
@@ -166,4 +173,6 @@ def test_deflines(lib):
     assert text(data) == (2, "ref|NP_000001.2| some protein\ngnl|mydb|7 another")
     assert text(data, gis=1)[1].startswith("gi|12345|ref|NP_000001.2| some protein")
     assert text(data, taxid=1)[1].startswith("ref|NP_000001.2||taxid|9606 some protein")
+    assert text(data, keep=[9606]) == (1, "ref|NP_000001.2| some protein")     # -x list: only that taxid's defline
+    assert text(data, keep=[1, 2])[0] == 0 and text(data, memb=2)[0] == 0
     assert text(b"\x31\x80\0\0")[0] == -7 and text(data[:20])[0] == -7      # not a defline set / truncated
