@@ -74,8 +74,10 @@ typedef struct swb_counters
   int64_t ref_width7;     /* subjects the reference would have kept from its 7-bit pass        */
   int64_t ref_width16;    /* ... from its 16-bit pass                                          */
   int64_t ref_width63;    /* ... from fullsw                                                   */
-  int64_t gpu_narrow;     /* subjects finished by the packed 16-bit-lane kernel                */
-  int64_t gpu_requeued;   /* subjects whose lane reached the overflow limit, redone wide       */
+  int64_t gpu_narrow;     /* subjects finished by the first packed kernel                         */
+  int64_t gpu_requeued;   /* subjects whose lane left the first kernel's exact range, re-queued  */
+  int64_t gpu_middle;     /* ... of those finished by the packed int16 build (the 16-bit tier);  */
+                          /* the remaining gpu_requeued - gpu_middle went to the wide kernel     */
   int64_t kernel_launches;/* CUDA kernels launched by this call                                */
   double scan_ms;         /* device time of the scan kernels (CUDA events on the handle stream)*/
   double requeue_ms;      /* device time of the wide re-queue kernels                          */

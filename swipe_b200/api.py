@@ -44,7 +44,7 @@ class _Scoring(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("subjects", C.c_int64), ("cells", C.c_int64), ("ref_width7", C.c_int64),
                 ("ref_width16", C.c_int64), ("ref_width63", C.c_int64), ("gpu_narrow", C.c_int64),
-                ("gpu_requeued", C.c_int64), ("kernel_launches", C.c_int64),
+                ("gpu_requeued", C.c_int64), ("gpu_middle", C.c_int64), ("kernel_launches", C.c_int64),
                 ("scan_ms", C.c_double), ("requeue_ms", C.c_double)]
 
     def as_dict(self):

@@ -660,17 +660,19 @@ __global__ void swb_partition_kernel(const long long *pairblk, long long npairs,
   stream_pair[s] = (int)lo;
 }
 
-// unpack lane maxima into per-subject scores; lanes at or above the limit are queued for the
-// wide kernel instead (the reference's re-queue, swipe.cc:1459-1479, :1514-1537)
+// unpack lane maxima into per-subject scores; lanes at or above the limit are queued for the next
+// wider pass instead (the reference's re-queue, swipe.cc:1459-1479, :1514-1537).  remap != NULL:
+// the layout was built over a re-queue list, entry k of it stands for position remap[k].
 __global__ void swb_finish_kernel(const u32 *pair_scores, const u32 *sorted_idx, long long n,
-                                  long long first, int limit, long long *scores,
+                                  long long first, int limit, const long long *remap, long long *scores,
                                   long long *requeue, unsigned long long *nrequeue)
 {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const u32 w = pair_scores[k >> 1];
   const int v = (int)((k & 1) ? (w >> 16) : (w & 0xffffu));
-  const long long pos = first + sorted_idx[k];   // position in the caller's list / shard
+  long long pos = first + sorted_idx[k];          // position in the caller's list / shard
+  if (remap) pos = remap[pos];
   if (v >= limit)
   {
     const unsigned long long slot = atomicAdd(nrequeue, 1ull);
@@ -678,6 +680,16 @@ __global__ void swb_finish_kernel(const u32 *pair_scores, const u32 *sorted_idx,
   }
   else
     scores[pos] = v;
+}
+
+// coded subject numbers (seqno << 3) of the positions queued for the next pass
+__global__ void swb_requeue_codes_kernel(const long long *requeue, long long n, const long long *list,
+                                         long long *codes)
+{
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const long long pos = requeue[k];
+  codes[k] = list ? (list[pos] & ~7ll) : (pos << 3);
 }
 
 // reference-width bookkeeping: which of the reference's passes would have kept each score

@@ -191,6 +191,8 @@ struct swb_db
   DevBuf<unsigned char> ttable;        // [4096] codon table
   std::vector<Layout *> chunks;   // the whole shard, cut into upload/layout/scan pipeline chunks
   Layout tmp;      // ad-hoc list layouts
+  Layout tmp2;     // the re-queue list of the 16-bit pass
+  DevBuf<long long> requeue2, codes;
   cudaStream_t copy_stream = nullptr, layout_stream = nullptr;
   cudaEvent_t ev_uploaded = nullptr;   // every byte of the shard is on the device
   cudaEvent_t ev_open[3] = {nullptr, nullptr, nullptr};
@@ -657,7 +659,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       {
         Layout *L = work[k];
         swb_finish_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(
-            L->pair_scores.p, L->idx_out.p, L->n, L->first, limit, db->scores.p, db->requeue.p,
+            L->pair_scores.p, L->idx_out.p, L->n, L->first, limit, nullptr, db->scores.p, db->requeue.p,
             db->counters.p);
         SWB_CUDA(cudaGetLastError());
         launches++;
@@ -672,8 +674,83 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     SWB_CUDA(cudaStreamSynchronize(st));
     nrequeue = (long long)h_nreq;
     SWB_CUDA(cudaEventRecord(db->ev[2], st));
-    SWB_TRY(run_wide(db, d_list, db->requeue.p, nrequeue, db->query.p, qlen, sc, false, use64,
-                     &launches));
+    const long long *wide_sel = db->requeue.p;
+    long long nwide = nrequeue;
+    if (nrequeue > 0 && mode == SWB_MODE_HYBRID && getenv("SWB_NO_MIDDLE") == nullptr)
+    {
+      // Middle tier of the cascade (the reference's 16-bit pass, swipe.cc:1483-1540): lanes that left
+      // the 11-bit range of the fp16-pattern build are scanned again by the pure int16 build (limit
+      // 32767 - hi) over a layout of just those subjects; only what overflows that goes to the wide
+      // kernel.
+      Tables t16;
+      int np16 = 1;
+      const ShapeEntry *sh16 = choose_shape(db, qlen, SWB_MODE_INT16, 0, 0, &np16);
+      if (!sh16) return SWB_ERR_INTERNAL;
+      const long long rows16 = (long long)np16 * sh16->G * sh16->R;
+      SWB_TRY(prepare_tables(t16, query, qlen, sc, SWB_MODE_INT16, (int)rows16));
+      SWB_TRY(db->codes.reserve((size_t)nrequeue));
+      SWB_TRY(db->requeue2.reserve((size_t)nrequeue));
+      SWB_TRY(db->qrow_off.reserve((size_t)rows16));
+      swb_requeue_codes_kernel<<<(unsigned)((nrequeue + 255) / 256), 256, 0, st>>>(db->requeue.p, nrequeue,
+                                                                                  d_list, db->codes.p);
+      SWB_CUDA(cudaGetLastError());
+      SWB_CUDA(cudaStreamWaitEvent(st, db->ev_uploaded, 0));
+      SWB_TRY(build_layout(db, db->tmp2, db->codes.p, 0, nrequeue, db->total_res, st));
+      launches += 6;
+      SWB_CUDA(cudaMemcpyAsync(db->m16.p, t16.m16.data(), t16.m16.size() * sizeof(short),
+                               cudaMemcpyHostToDevice, st));
+      SWB_CUDA(cudaMemcpyAsync(db->qrow_off.p, t16.qrow.data(), t16.qrow.size() * sizeof(unsigned short),
+                               cudaMemcpyHostToDevice, st));
+      SWB_CUDA(cudaMemsetAsync(db->counters.p, 0, sizeof(unsigned long long), st));
+      const int threads16 = swb_scan_threads(sh16->G);
+      const size_t smem16 = swb_scan_smem(sh16->G, t16.nq);
+      const scan_fn fn16 = np16 > 1 ? sh16->fn_mp : sh16->fn;
+      SWB_CUDA(cudaFuncSetAttribute((const void *)fn16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+      int occ16 = 0;
+      SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ16, (const void *)fn16, threads16, smem16));
+      if (occ16 < 1) return SWB_ERR_INTERNAL;
+      // few subjects: no more streams than pairs (a stream walks its pairs one after the other)
+      Layout &L2 = db->tmp2;
+      int grid16 = db->sm_count * occ16;
+      grid16 = (int)std::max<long long>(1, std::min<long long>(grid16, (L2.npairs + SWB_STREAMS - 1) / SWB_STREAMS));
+      const int nstreams16 = grid16 * SWB_STREAMS;
+      SWB_TRY(L2.stream_pair.reserve((size_t)nstreams16 + 1));
+      swb_partition_kernel<<<(nstreams16 + 1 + 255) / 256, 256, 0, st>>>(L2.pairblk.p, L2.npairs, nstreams16,
+                                                                         L2.stream_pair.p);
+      SWB_CUDA(cudaGetLastError());
+      L2.stream_pair_n = nstreams16;
+      SWB_CUDA(cudaMemsetAsync(L2.pair_scores.p, 0, (size_t)L2.npairs * sizeof(u32), st));
+      if (np16 > 1)
+      {
+        SWB_TRY(db->bndH.reserve((size_t)L2.cap_blocks));
+        SWB_TRY(db->bndF.reserve((size_t)L2.cap_blocks));
+      }
+      ScanParams P2;
+      memset(&P2, 0, sizeof P2);
+      P2.seg.blocks = L2.blocks.p; P2.seg.pairblk = L2.pairblk.p; P2.seg.stream_pair = L2.stream_pair.p;
+      P2.seg.pair_scores = L2.pair_scores.p; P2.seg.bnd_base = 0;
+      P2.m16 = db->m16.p; P2.qrow_off = db->qrow_off.p; P2.bndH = db->bndH.p; P2.bndF = db->bndF.p;
+      P2.nq = t16.nq; P2.npass = np16;
+      const unsigned q16 = (unsigned)(unsigned short)enc16(-sc->gap_open_extend, SWB_MODE_INT16);
+      const unsigned r16 = (unsigned)(unsigned short)(short)(-sc->gap_extend);
+      const unsigned p16 = (unsigned)(unsigned short)enc16(SWB_PAD_SCORE, SWB_MODE_INT16);
+      P2.negq = q16 | (q16 << 16); P2.negr = r16 | (r16 << 16); P2.padword = p16 | (p16 << 16);
+      fn16<<<grid16, threads16, smem16, st>>>(P2);
+      SWB_CUDA(cudaGetLastError());
+      const int limit16 = 32767 - (int)std::max<long long>(tb.hi, 0);
+      swb_finish_kernel<<<(unsigned)((nrequeue + 255) / 256), 256, 0, st>>>(
+          L2.pair_scores.p, L2.idx_out.p, nrequeue, 0, limit16, db->requeue.p, db->scores.p, db->requeue2.p,
+          db->counters.p);
+      SWB_CUDA(cudaGetLastError());
+      launches += 4;
+      unsigned long long h_n2 = 0;
+      SWB_CUDA(cudaMemcpyAsync(&h_n2, db->counters.p, sizeof h_n2, cudaMemcpyDeviceToHost, st));
+      SWB_CUDA(cudaStreamSynchronize(st));
+      nwide = (long long)h_n2;
+      wide_sel = db->requeue2.p;
+      c.gpu_middle = nrequeue - nwide;
+    }
+    SWB_TRY(run_wide(db, d_list, wide_sel, nwide, db->query.p, qlen, sc, false, use64, &launches));
     SWB_CUDA(cudaEventRecord(db->ev[3], st));
   }
   else
@@ -1182,7 +1259,8 @@ int swb_db_close(swb_db *db)
   if (db->copy_stream) cudaStreamSynchronize(db->copy_stream);
   if (db->layout_stream) cudaStreamSynchronize(db->layout_stream);
   if (db->stream) cudaStreamSynchronize(db->stream);
-  db->residues.release(); db->offsets.release(); db->tmp.release();
+  db->residues.release(); db->offsets.release(); db->tmp.release(); db->tmp2.release();
+  db->requeue2.release(); db->codes.release();
   db->packed.release(); db->pk_start.release(); db->pk_len.release();
   db->nt_residues.release(); db->nt_offsets.release(); db->ttable.release();
   for (Layout *L : db->chunks) { L->release(); delete L; }

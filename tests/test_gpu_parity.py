@@ -86,7 +86,40 @@ def test_requeue_limits(oracle):
             got, c = _check(db, q, sc, oracle, residues, offsets, "requeue mode %d" % lane_mode)
             assert c["gpu_requeued"] == int((got >= limit).sum())
             assert c["gpu_narrow"] + c["gpu_requeued"] == got.size
+            if lane_mode == 1:       # the 16-bit tier takes what fits int16 lanes, the wide kernel the rest
+                assert c["gpu_middle"] == int(((got >= limit) & (got < 32767 - 11)).sum()) > 0
+                assert c["gpu_requeued"] - c["gpu_middle"] == int((got >= 32767 - 11).sum()) > 0
+            else:
+                assert c["gpu_middle"] == 0
         assert got.max() > 32767
+        # the same through a list search (positions of the re-queue are list positions)
+        db.set_shape(0, 0, -1)
+        sel = np.arange(len(subs) - 1, -1, -3)
+        exp, _, _ = oracle.scan(residues, offsets, q, B62, 11, 1)
+        assert np.array_equal(db.search_list(q, sc, sel), exp[sel])
+        assert db.last_counters["gpu_middle"] > 0
+
+
+def test_many_requeued_subjects(oracle):
+    """A database where a fifth of the subjects score above the 11-bit range (long self copies):
+    the 16-bit tier handles a re-queue list of hundreds of subjects in one launch."""
+    rng = np.random.default_rng(15)
+    q = synth.protein_query(900, seed=78)
+    subs = []
+    for i in range(1500):
+        if i % 5 == 0:
+            a = int(rng.integers(0, 200))
+            piece = q[a:a + int(rng.integers(450, 700))].copy()
+            mut = rng.random(piece.size) < 0.05
+            piece[mut] = synth.random_protein(rng, int(mut.sum()))
+            subs.append(np.concatenate([synth.random_protein(rng, int(rng.integers(0, 30))), piece]))
+        else:
+            subs.append(synth.random_protein(rng, int(rng.integers(20, 600))))
+    residues, offsets = fixtures.pack(subs)
+    sc = Scoring(B62, 11, 1)
+    with Database(residues, offsets) as db:
+        got, c = _check(db, q, sc, oracle, residues, offsets, "many requeued")
+        assert c["gpu_requeued"] >= 250 and c["gpu_middle"] == c["gpu_requeued"]
 
 
 def test_wide_only_matches(oracle):
