@@ -67,6 +67,33 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
 
     def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
+    def _run_nvml(self):
+        """NVML directly (nvidia-ml-py): a sample every 20 ms instead of one per nvidia-smi start-up."""
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            while not self._halt.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self._halt.wait(0.02)
+        finally:
+            pynvml.nvmlShutdown()
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
