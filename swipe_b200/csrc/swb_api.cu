@@ -863,6 +863,95 @@ int swb_host_free(void *ptr)
   return SWB_OK;
 }
 
+// Uploads from PAGEABLE host memory (a memory-mapped database file, a plain malloc) go through a few
+// pinned staging buffers filled by a handful of host threads: cudaMemcpyAsync on pageable memory
+// stages through the driver at a few GB/s, which would make opening a shard cost several scans.
+// Used by the synchronous opens only (the asynchronous open must return at once and documents that
+// its buffers should be pinned).
+struct Stager
+{
+  static const int NBUF = 4;
+  static const size_t BUF = (size_t)32 << 20;
+  std::mutex mu;
+  unsigned char *buf[NBUF] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t done[NBUF] = {nullptr, nullptr, nullptr, nullptr};
+  bool used[NBUF] = {false, false, false, false};
+  int next = 0;
+  bool ready = false, broken = false;
+
+  bool init()
+  {
+    if (ready || broken) return ready;
+    for (int i = 0; i < NBUF; i++)
+      if (cudaHostAlloc((void **)&buf[i], BUF, cudaHostAllocPortable) != cudaSuccess ||
+          cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
+      {
+        (void)cudaGetLastError();
+        broken = true;
+        return false;
+      }
+    ready = true;
+    return true;
+  }
+
+  static void parallel_copy(unsigned char *dst, const unsigned char *src, size_t n)
+  {
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(hw ? hw : 1, 6), n >> 22));
+    if (nt == 1) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < nt; t++)
+      pool.emplace_back([=]() { memcpy(dst + n * t / nt, src + n * t / nt, n * (t + 1) / nt - n * t / nt); });
+    for (std::thread &t : pool) t.join();
+  }
+
+  // dst (device) <- src (pageable host), enqueued on st; returns a CUDA error code
+  cudaError_t copy(unsigned char *dst, const unsigned char *src, size_t n, cudaStream_t st)
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (!init()) return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st);
+    for (size_t off = 0; off < n; off += BUF)
+    {
+      const size_t len = std::min(BUF, n - off);
+      const int k = next;
+      next = (next + 1) % NBUF;
+      if (used[k])
+      {
+        cudaError_t e = cudaEventSynchronize(done[k]);      // the copy that last used this buffer
+        if (e != cudaSuccess) return e;
+      }
+      parallel_copy(buf[k], src + off, len);
+      cudaError_t e = cudaMemcpyAsync(dst + off, buf[k], len, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+      e = cudaEventRecord(done[k], st);
+      if (e != cudaSuccess) return e;
+      used[k] = true;
+    }
+    return cudaSuccess;
+  }
+
+  // before another device's stream reuses the buffers
+  void drain()
+  {
+    std::lock_guard<std::mutex> g(mu);
+    for (int i = 0; i < NBUF; i++)
+      if (used[i]) { cudaEventSynchronize(done[i]); used[i] = false; }
+  }
+};
+Stager g_stagers[64];               // one per device: events and streams must share a device
+inline Stager &stager_of(int device) { return g_stagers[device & 63]; }
+
+bool is_pageable(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+  {
+    (void)cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
 // Where the subjects of a shard come from.  `offsets` are byte offsets of the (decoded) residues
 // in the device residue buffer; `extents` name the host memory holding contiguous runs of subjects:
 // raw symbol bytes (copied as they are) or .nsq records (copied to the packed buffer and decoded on
@@ -997,8 +1086,14 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
         const long long a = std::max(lo, E.s0), b = std::min(hi, E.s1);
         const long long bytes = coord[b] - coord[a];
         if (bytes > 0)
-          SWB_CUDA(cudaMemcpyAsync(dst_base + coord[a], E.src + (coord[a] - coord[E.s0]), (size_t)bytes,
-                                   cudaMemcpyHostToDevice, db->copy_stream));
+        {
+          const uint8_t *src = E.src + (coord[a] - coord[E.s0]);
+          if (wait && bytes >= (8 << 20) && getenv("SWB_NO_STAGING") == nullptr && is_pageable(src))
+            SWB_CUDA(stager_of(db->device).copy(dst_base + coord[a], src, (size_t)bytes, db->copy_stream));
+          else
+            SWB_CUDA(cudaMemcpyAsync(dst_base + coord[a], src, (size_t)bytes, cudaMemcpyHostToDevice,
+                                     db->copy_stream));
+        }
       }
       SWB_CUDA(cudaEventCreateWithFlags(&L->ev_ready, cudaEventDisableTiming));
       cudaEvent_t up;
@@ -1038,7 +1133,11 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
     SWB_CUDA(cudaEventRecord(db->ev_uploaded, db->copy_stream));
     SWB_CUDA(cudaEventRecord(db->ev_open[2], db->layout_stream));
     if (db->chunks.empty()) SWB_CUDA(cudaEventRecord(db->ev_open[1], db->layout_stream));
-    if (wait) SWB_TRY(swb_db_wait(db));
+    if (wait)
+    {
+      SWB_TRY(swb_db_wait(db));
+      stager_of(db->device).drain();
+    }
     return SWB_OK;
   };
   const int rc = body();
