@@ -194,6 +194,8 @@ struct swb_db
   Layout tmp2;     // the re-queue list of the 16-bit pass
   DevBuf<long long> requeue2, codes;
   cudaStream_t copy_stream = nullptr, layout_stream = nullptr;
+  cudaStream_t stream2 = nullptr;      // second compute stream: overlapping launches while the shard arrives
+  cudaEvent_t ev_setup = nullptr;
   cudaEvent_t ev_uploaded = nullptr;   // every byte of the shard is on the device
   cudaEvent_t ev_open[3] = {nullptr, nullptr, nullptr};
   bool opened_sync = false;
@@ -621,11 +623,20 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     P.nq = tb.nq; P.npass = npass;
     P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
     SWB_CUDA(cudaEventRecord(db->ev[0], st));
+    // While the shard is arriving, consecutive groups alternate between two streams: the CTAs of the
+    // next launch fill the SMs as those of the previous one drain, so the launch boundary costs nothing.
+    const bool two_streams = !resident && db->stream2 && getenv("SWB_ONE_STREAM") == nullptr;
+    if (two_streams)
+    {
+      SWB_CUDA(cudaEventRecord(db->ev_setup, st));               // tables, chunk table, counters are set up on st
+      SWB_CUDA(cudaStreamWaitEvent(db->stream2, db->ev_setup, 0));
+    }
     size_t next = 0;
     int group_no = 0;
     while (next < work.size())
     {
       size_t end = next + 1;
+      cudaStream_t gs = (two_streams && (group_no & 1)) ? db->stream2 : st;
       if (!resident)
       {
         if (group_no >= 2) SWB_CUDA(cudaEventSynchronize(db->ev_group[group_no & 1]));   // group_no - 2 is done
@@ -639,35 +650,37 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       for (size_t k = next; k < end; k++)
       {
         Layout *L = work[k];
-        if (L->ev_ready) SWB_CUDA(cudaStreamWaitEvent(st, L->ev_ready, 0));
+        if (L->ev_ready) SWB_CUDA(cudaStreamWaitEvent(gs, L->ev_ready, 0));
         if (L->stream_pair_n != nstreams)
         {
-          swb_partition_kernel<<<(nstreams + 1 + 255) / 256, 256, 0, st>>>(L->pairblk.p, L->npairs,
+          swb_partition_kernel<<<(nstreams + 1 + 255) / 256, 256, 0, gs>>>(L->pairblk.p, L->npairs,
                                                                            nstreams, L->stream_pair.p);
           SWB_CUDA(cudaGetLastError());
           launches++;
           L->stream_pair_n = nstreams;
         }
-        SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * sizeof(u32), st));
+        SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * sizeof(u32), gs));
       }
       P.seg = segs[next];
       P.segs = db->segs.p + next;
-      fn<<<dim3((unsigned)grid, (unsigned)(end - next)), threads, smem, st>>>(P);
+      fn<<<dim3((unsigned)grid, (unsigned)(end - next)), threads, smem, gs>>>(P);
       SWB_CUDA(cudaGetLastError());
       launches++;
       for (size_t k = next; k < end; k++)
       {
         Layout *L = work[k];
-        swb_finish_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(
+        swb_finish_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, gs>>>(
             L->pair_scores.p, L->idx_out.p, L->n, L->first, limit, nullptr, db->scores.p, db->requeue.p,
             db->counters.p);
         SWB_CUDA(cudaGetLastError());
         launches++;
       }
-      if (!resident) SWB_CUDA(cudaEventRecord(db->ev_group[group_no & 1], st));
+      if (!resident) SWB_CUDA(cudaEventRecord(db->ev_group[group_no & 1], gs));
       group_no++;
       next = end;
     }
+    if (two_streams && group_no >= 2)
+      SWB_CUDA(cudaStreamWaitEvent(st, db->ev_group[1], 0));     // the last launch on stream2 (odd groups)
     SWB_CUDA(cudaEventRecord(db->ev[1], st));
     unsigned long long h_nreq = 0;
     SWB_CUDA(cudaMemcpyAsync(&h_nreq, db->counters.p, sizeof h_nreq, cudaMemcpyDeviceToHost, st));
@@ -1037,6 +1050,8 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
     }
     SWB_CUDA(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
     SWB_CUDA(cudaStreamCreateWithFlags(&db->layout_stream, cudaStreamNonBlocking));
+    SWB_CUDA(cudaStreamCreateWithFlags(&db->stream2, cudaStreamNonBlocking));
+    SWB_CUDA(cudaEventCreateWithFlags(&db->ev_setup, cudaEventDisableTiming));
     for (int i = 0; i < 4; i++) SWB_CUDA(cudaEventCreate(&db->ev[i]));
     for (int i = 0; i < 2; i++) SWB_CUDA(cudaEventCreateWithFlags(&db->ev_group[i], cudaEventDisableTiming));
     for (int i = 0; i < 3; i++) SWB_CUDA(cudaEventCreate(&db->ev_open[i]));
@@ -1357,6 +1372,7 @@ int swb_db_close(swb_db *db)
   cudaSetDevice(db->device);
   if (db->copy_stream) cudaStreamSynchronize(db->copy_stream);
   if (db->layout_stream) cudaStreamSynchronize(db->layout_stream);
+  if (db->stream2) cudaStreamSynchronize(db->stream2);
   if (db->stream) cudaStreamSynchronize(db->stream);
   db->residues.release(); db->offsets.release(); db->tmp.release(); db->tmp2.release();
   db->requeue2.release(); db->codes.release();
@@ -1377,6 +1393,8 @@ int swb_db_close(swb_db *db)
   if (db->ev_uploaded) cudaEventDestroy(db->ev_uploaded);
   if (db->copy_stream) cudaStreamDestroy(db->copy_stream);
   if (db->layout_stream) cudaStreamDestroy(db->layout_stream);
+  if (db->stream2) { cudaStreamSynchronize(db->stream2); cudaStreamDestroy(db->stream2); }
+  if (db->ev_setup) cudaEventDestroy(db->ev_setup);
   if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
   delete db;
   (void)cudaGetLastError();

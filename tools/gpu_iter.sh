@@ -1,22 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log | cut -c1-300
-python - <<'PY'
-import sys, time, os
-sys.path.insert(0, '.')
-import numpy as np
-from swipe_b200 import Database, Scoring, scoring, synth
-q = synth.protein_query(375)
-res, off = synth.protein_db(5000000, query=q)
-sc = Scoring(scoring.blosum62(), 11, 1)
-for env in ("1", None, None):
-    if env: os.environ["SWB_NO_STAGING"] = env
-    else: os.environ.pop("SWB_NO_STAGING", None)
-    t = time.perf_counter()
-    db = Database(res, off)
-    t1 = time.perf_counter() - t
-    s = db.search(q, sc)
-    print("staging" if env is None else "no staging", "open %.1f ms" % (t1 * 1e3), "open_ms", db.open_ms(), int(s.sum()))
-    db.close()
-PY
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_blastdb.py -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log | cut -c1-300
+for v in "SWB_ONE_STREAM=1" "SWB_X=1" "SWB_ONE_STREAM=1" "SWB_X=1"; do
+  echo "== $v"; env $v python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e']['host_ms'])"
+done
