@@ -275,3 +275,36 @@ def test_chunked_async_open(oracle, monkeypatch):
                 assert np.array_equal(db.search_list(q, sc, sel), exp[sel])
                 db.set_shape(8, 8, 1)                     # multi-pass over chunks
                 assert np.array_equal(db.search(q, sc), exp)
+
+
+def test_random_scoring_systems(oracle):
+    """Seeded fuzz: random (asymmetric) tables over random symbol subsets, random gap penalties, query
+    lengths and subject sets, through whatever shape / lane mode / cascade tier the library picks."""
+    rng = np.random.default_rng(20261017)
+    for it in range(24):
+        ncodes = int(rng.integers(2, 32))
+        codes = rng.permutation(32)[:ncodes]
+        m = np.full((32, 32), -1, dtype=np.int64)
+        lo, hi = int(rng.integers(-12, 0)), int(rng.integers(1, 16))
+        m[np.ix_(codes, codes)] = rng.integers(lo, hi + 1, size=(ncodes, ncodes))
+        if it % 3 == 0:
+            for c in codes:
+                m[c, c] = hi
+        go, ge = int(rng.integers(0, 25)), int(rng.integers(0, 6))
+        if go + ge == 0:
+            ge = 1
+        qlen = int(rng.choice([1, 3, 17, 64, 100, 333, 700]))
+        q = rng.choice(codes, size=qlen).astype(np.uint8)
+        subs = []
+        for _ in range(150):
+            L = int(rng.integers(0, 500))
+            s = rng.choice(codes, size=L).astype(np.uint8)
+            if L > 20 and qlen > 8 and rng.random() < 0.2:
+                w = int(min(L, qlen, rng.integers(8, 300)))
+                a = int(rng.integers(0, qlen - w + 1))
+                s[:w] = q[a:a + w]
+            subs.append(s)
+        subs.append(rng.integers(0, 32, size=77).astype(np.uint8))          # symbols outside the table
+        residues, offsets = fixtures.pack(subs)
+        with Database(residues, offsets) as db:
+            _check(db, q, Scoring(m.reshape(-1), go, ge), oracle, residues, offsets, "fuzz %d" % it)
