@@ -31,6 +31,7 @@ typedef unsigned long long u64;
 #define SWB_PAD_SCORE (-1)
 #define SWB_MROWS 33         // 32 symbol codes + the pad code
 #define SWB_SMEM_HEADER 2304  // the staged [33][34] s16 score matrix, rounded up to 128 B
+#define SWB_M16_BYTES 2256    // its image in global memory: 33 * 34 halfwords padded to a multiple of 16 B
 #define SWB_FLAG_START 1u
 #define SWB_FLAG_END 2u
 
@@ -52,7 +53,8 @@ struct ScanParams
 {
   ScanSeg seg;
   const ScanSeg *segs;        // [gridDim.y] device array, or NULL: use seg
-  const short *m16;           // [33][32] score of (subject code, table row) in the mode's encoding
+  const short *m16;           // [33][34] (SWB_M16_BYTES) score of (subject code, table row) in the mode's
+                              // encoding, laid out as it is staged in shared memory
   const unsigned short *qrow_off; // [npass*G*R] 16 * (table row of every query row)
   uint4 *bndH;                // [total_blocks] bottom H of a pass (only when npass > 1)
   uint4 *bndF;
@@ -224,8 +226,20 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   const u32 zbox = ring + ring_bytes;                         // 8 all-zero mailbox entries
   const u32 xfer = zbox + SWB_STREAMS * SWB_XFER_BYTES;       // [2][NWARP][8] entries of 48 B
 
-  for (int i = tid; i < SWB_MROWS * 32; i += blockDim.x)
-    swb_sts16(sbase + 2u * (u32)((i >> 5) * SWB_MS_STRIDE + (i & 31)), ((const unsigned short *)P.m16)[i]);
+  // The score profile is staged once per CTA by the bulk-copy engine (TMA, cp.async.bulk): one thread
+  // arms an mbarrier with the byte count and issues the copy; everybody waits on the barrier's phase
+  // after the rest of the set-up below.
+  __shared__ __align__(8) unsigned long long tma_bar;
+  const u32 bar = (u32)__cvta_generic_to_shared(&tma_bar);
+  if (tid == 0)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((u32)SWB_M16_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sbase), "l"(__cvta_generic_to_global(P.m16)), "r"((u32)SWB_M16_BYTES), "r"(bar) : "memory");
+  }
   // header rows start out flag-free; the pad row of every slot is written once and never rebuilt
   for (int i = tid; i < NSLOT * SWB_STREAMS; i += blockDim.x)
   {
@@ -234,7 +248,16 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
     swb_sts128(base + (u32)(nq + 1) * 128u, make_uint4(P.padword, P.padword, P.padword, P.padword));
   }
   for (int i = tid; i < SWB_STREAMS * SWB_XFER_BYTES / 4; i += blockDim.x) swb_sts32(zbox + 4u * i, 0);
-  __syncthreads();
+  __syncthreads();                                            // also publishes the mbarrier's initialisation
+  {
+    u32 done = 0;
+    for (int spins = 0; !done; spins++)
+    {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar) : "memory");
+      if (spins > (1 << 24)) __trap();                        // a copy that never lands must not hang the GPU
+    }
+  }
 
   ScanSeg S = P.seg;
   if (P.segs) S = P.segs[blockIdx.y];

@@ -278,7 +278,7 @@ struct Tables
   long long limit7 = 0, limit16 = 0;
   bool narrow_ok = false;      // the packed kernels can represent this scoring system
   bool hybrid_ok = false;
-  std::vector<short> m16;      // [33][32]
+  std::vector<short> m16;      // [33][34] + padding = SWB_M16_BYTES, the image staged in shared memory
   std::vector<unsigned short> qrow;
 };
 
@@ -310,7 +310,7 @@ int prepare_tables(Tables &t, const unsigned char *query, long long qlen, const 
   t.narrow_ok = t.nq <= 30 && t.hi <= 1024 && t.lo >= -1024 && q >= 0 && q <= 8192 && r >= 0 &&
                 r <= 8192;
   t.hybrid_ok = t.narrow_ok && t.hi <= 256 && t.lo >= -1023 && q <= 1023 && r <= 1023;
-  t.m16.assign(SWB_MROWS * 32, 0);
+  t.m16.assign(SWB_M16_BYTES / sizeof(short), 0);
   for (int d = 0; d < SWB_MROWS; d++)
     for (int s = 0; s < 32; s++)
     {
@@ -318,7 +318,7 @@ int prepare_tables(Tables &t, const unsigned char *query, long long qlen, const 
       if (d < 32)
         for (int qs = 0; qs < 32; qs++)
           if (t.rowof[qs] == s) v = sc->matrix[(d << 5) + qs];
-      t.m16[d * 32 + s] = t.narrow_ok ? enc16(v, mode) : (short)0;
+      t.m16[d * SWB_MS_STRIDE + s] = t.narrow_ok ? enc16(v, mode) : (short)0;
     }
   t.qrow.assign((size_t)rows_padded, (unsigned short)((t.nq + 1) * 16));
   for (long long i = 0; i < qlen && i < rows_padded; i++)
@@ -561,7 +561,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     for (Layout *L : layouts) min_blocks = std::max(min_blocks, L->cap_blocks);
     while (oversub > 1 && min_blocks / ((long long)db->sm_count * occ * oversub * SWB_STREAMS) < 40 * shape->G)
       oversub--;                                   // keep streams much longer than the pipeline fill
-    SWB_TRY(db->m16.reserve(SWB_MROWS * 32));
+    SWB_TRY(db->m16.reserve(SWB_M16_BYTES / sizeof(short)));
     SWB_TRY(db->qrow_off.reserve((size_t)rows_padded));
     SWB_CUDA(cudaMemcpyAsync(db->m16.p, tb.m16.data(), tb.m16.size() * sizeof(short),
                              cudaMemcpyHostToDevice, st));
