@@ -152,9 +152,10 @@ def run_reference_cpu(q, residues, offsets, budget_s, threads):
     rate = float(offsets[n0]) * q.size / max(t1 - t0, 1e-6)          # cells / s, cold
     n = int(min(nseq, max(n0, budget_s * rate / (q.size * (offsets[n0] / n0)))))
     t0 = time.perf_counter()
-    scan(n)
+    out = scan(n)
     t1 = time.perf_counter()
     cells = float(offsets[n]) * q.size
+    run_reference_cpu.last_scores = np.asarray(out[0][:n])      # kept for the bench's full-size parity check
     return cells / (t1 - t0) * 1e-9, kind, "first %d subjects (%d residues) of the shard, %.1f s" % (
         n, int(offsets[n]), t1 - t0)
 
@@ -405,6 +406,12 @@ def main():
             g, kind, desc = run_reference_cpu(q, residues, offsets, 12.0, cores)
             line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": kind,
                                     "sample": desc}
+            # the CPU leg scored the same subjects: a bit-exact parity check at the bench's full size
+            ref_scores = getattr(run_reference_cpu, "last_scores", None)
+            if ref_scores is not None:
+                k = int(ref_scores.size)
+                line["cpu_baseline"]["scores_compared"] = k
+                line["cpu_baseline"]["scores_equal"] = bool(np.array_equal(ref_scores, scores[:k]))
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
