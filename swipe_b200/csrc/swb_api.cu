@@ -1489,7 +1489,7 @@ int64_t swb_topk_merge(int nshards, const int64_t *const *scores, const int64_t 
   // large shards are cut over a few host threads; every piece keeps its own top `keep`
   struct Piece { int shard; int64_t lo, hi; };
   std::vector<Piece> pieces;
-  const int64_t grain = 1 << 20;
+  const int64_t grain = 1 << 18;
   unsigned hw = std::thread::hardware_concurrency();
   const int64_t maxpar = std::max<int64_t>(1, std::min<int64_t>(hw ? hw : 1, 8));
   for (int s = 0; s < nshards; s++)
