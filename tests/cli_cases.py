@@ -110,6 +110,8 @@ CASES = {
     "protein_minscore_nolimit": "-d p -i q.fa -e 1e30 -c 30 -u 600 -m 7 -b 0 -v 1000",
     "protein_custom_matrix": "-d p -i q.fa -M asym.mat -G 7 -E 2 -v 12 -b 4",
     "protein_effdbsize": "-d p -i q.fa -z 5000000 -m 8 -b 10",
+    "protein_min_evalue": "-d p -i q.fa -k 1e-100 -e 1e30 -m 8 -b 12",
+    "protein_long_options": "--db=p --query=q.fa --matrix=BLOSUM80 --gapopen=10 --gapextend=1 --outfmt=8 --num_alignments=9 --evalue=1e-3",
     "annotated_plain": "-d px -i q.fa -e 1e30 -v 12 -b 3 -I -H",
     "annotated_tsv": "-d px -i q.fa -e 1e30 -m 8 -b 45",
     "taxid_list": "-d px -i q.fa -e 1e30 -x tax.txt -m 8 -b 45",

@@ -50,3 +50,14 @@ def test_cli_two_gpus_same_output_as_one(workdir):
         outs.append(r.stdout)
     assert outs[0] == outs[1] == outs[2]
     assert cli_cases.normalise(outs[0]) == open(os.path.join(GOLD, "protein_tsv.txt")).read()
+
+
+def test_cli_stdin_query_and_output_file(workdir):
+    """-i - reads the query from stdin (the default, swipe.cc:34) and -o writes the report to a file."""
+    exe = build.build_cli()
+    q = open(os.path.join(workdir, "q.fa")).read()
+    r = subprocess.run([exe] + "-d p -m 8 -b 40 -o out.tsv".split(), cwd=workdir, input=q, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout == "", r.stderr
+    got = cli_cases.normalise(open(os.path.join(workdir, "out.tsv")).read())
+    assert got == open(os.path.join(GOLD, "protein_tsv.txt")).read()
