@@ -13,11 +13,11 @@ import blastdb
 from swipe_b200 import BlastDB, Database, Scoring, scoring, synth
 
 os.environ["SWB_CHUNK_BYTES"] = "20000"
-q = synth.protein_query(300)
+q = synth.protein_query(500)
 res, off = synth.protein_db(400, query=q, seed=3, plant_every=7, max_len=500)
-# a long self copy so that the middle tier and the wide kernel run
-res = np.concatenate([res, np.tile(q, 8)])
-off = np.concatenate([off, [off[-1] + 8 * q.size]])
+# a self copy scores above the 11-bit range: the int16 middle tier runs; mode 2 below runs the wide kernel
+res = np.concatenate([res, q])
+off = np.concatenate([off, [off[-1] + q.size]])
 sc = Scoring(scoring.blosum62(), 11, 1)
 with Database(res, off) as db:
     a = db.search(q, sc)
@@ -25,7 +25,11 @@ with Database(res, off) as db:
     b = db.search(q, sc)                      # multi-pass
     assert np.array_equal(a, b)
     db.set_shape(0, 0, -1)
+    assert db.last_counters["gpu_middle"] >= 1
     s, bp, bq = db.search_end(q, sc, np.arange(0, 400, 40))
+    db.set_mode(2)
+    w = db.search_list(q, sc, np.arange(380, 401))
+    assert np.array_equal(w, a[380:401])
     print("protein ok", int(a.max()), db.last_counters)
 with Database(res, off, wait=False) as db:
     assert np.array_equal(db.search(q, sc), a)
