@@ -204,6 +204,7 @@ int swb_search_end(swb_db *db, const uint8_t *query, int64_t qlen, const swb_sco
 int swb_matrix_builtin(const char *name, int64_t *matrix);        /* BLOSUM45/50/62/80/90, PAM30/70/250, identity_5_1 */
 int swb_matrix_parse(const char *text, int64_t *matrix);          /* matrix file text (matrices.cc:437-517) */
 int swb_matrix_read(const char *name_or_path, int64_t *matrix);   /* built-in name, else a file */
+int swb_matrix_read_sound(const char *name_or_path, int64_t *matrix);   /* -p 5: IDENTITY_5_1 or a file in the sound alphabet */
 int swb_matrix_nucleotide(int64_t match, int64_t mismatch, int64_t *matrix);   /* matrices.cc:533-538 */
 int swb_matrix_limits(const int64_t *matrix, int64_t *lo, int64_t *hi, int64_t *limit7, int64_t *limit16);
 
@@ -232,7 +233,8 @@ double swb_stats_evalue(const swb_stats *st, int64_t score);     /* Kmn * exp(-l
 double swb_stats_bits(const swb_stats *st, int64_t score);       /* (lambda * score - ln K) / ln 2 */
 
 /* ---- query text, translation, deflines (host) ------------------------------------------------ */
-/* One FASTA record -> symbol codes (query.cc:244-355); returns the bytes of text consumed.       */
+/* One FASTA record -> symbol codes (query.cc:244-355); returns the bytes of text consumed.
+ * nucleotide: 0 = amino acids, 1 = nucleotides, 2 = the sound alphabet of -p 5.                  */
 int64_t swb_query_parse(const char *text, int64_t text_len, int nucleotide, uint8_t *seq,
                         int64_t seq_cap, int64_t *seq_len, char *descr, int64_t descr_cap);
 int swb_revcomp(const uint8_t *seq, int64_t len, uint8_t *out);   /* 4-bit nt codes (query.cc:357-364) */

@@ -20,11 +20,11 @@ EXPORTS = ["swb_abi_version", "swb_align", "swb_blastdb_close", "swb_blastdb_dat
            "swb_db_wait", "swb_defline_text", "swb_device_count", "swb_gencode_name",
            "swb_host_alloc", "swb_host_free", "swb_last_cuda_error", "swb_matrix_builtin",
            "swb_matrix_limits", "swb_matrix_nucleotide", "swb_matrix_parse", "swb_matrix_read",
-           "swb_query_parse", "swb_revcomp", "swb_search", "swb_search_end",
-           "swb_search_list", "swb_set_mode", "swb_set_shape", "swb_stats_bits",
-           "swb_stats_default_gaps", "swb_stats_evalue", "swb_stats_init", "swb_stats_length_adjustment",
-           "swb_stats_params", "swb_stats_params_nt", "swb_strerror", "swb_topk_merge",
-           "swb_translate", "swb_translate_table", "swb_trim"]
+           "swb_matrix_read_sound", "swb_query_parse", "swb_revcomp", "swb_search",
+           "swb_search_end", "swb_search_list", "swb_set_mode", "swb_set_shape",
+           "swb_stats_bits", "swb_stats_default_gaps", "swb_stats_evalue", "swb_stats_init",
+           "swb_stats_length_adjustment", "swb_stats_params", "swb_stats_params_nt", "swb_strerror",
+           "swb_topk_merge", "swb_translate", "swb_translate_table", "swb_trim"]
 
 
 class SwbError(RuntimeError):

@@ -67,6 +67,53 @@ long long length_adjustment(double K, double logK, double a_d_l, double beta, do
   return adj;
 }
 
+// the "sound" alphabet of -p 5 (query.cc:31-49): A-Z = 1..26, a-e = 27..31
+int sound_code(int c)
+{
+  if (c >= 'A' && c <= 'Z') return c - 'A' + 1;
+  if (c >= 'a' && c <= 'e') return c - 'a' + 27;
+  return -1;
+}
+
+// The text format of matrix files (matrices.cc:437-517): '#' comments; a line starting with a
+// blank lists the column symbols; every other line is "<row symbol> <score> <score> ...".  The
+// first symbol of a data line is the first index, i.e. entry [(row << 5) + column].
+int matrix_parse(const char *text, int64_t *m, int (*code_of)(int))
+{
+  if (!text || !m) return SWB_ERR_ARG;
+  for (int i = 0; i < 1024; i++) m[i] = -1;
+  int order[4096], nsym = 0;
+  const char *s = text;
+  while (*s)
+  {
+    const char *e = strchr(s, '\n');
+    std::string line = e ? std::string(s, e - s) : std::string(s);
+    s = e ? e + 1 : s + line.size();
+    if (line.empty()) continue;
+    const char c = line[0];
+    if (c == '#' || c == '\n') continue;
+    if (c == ' ' || c == '\t')
+    {
+      for (size_t k = 1; k < line.size(); k++)
+        if (!strchr(" \t\n", line[k]) && nsym < 4096) order[nsym++] = code_of((unsigned char)line[k]);
+      continue;
+    }
+    const int a = code_of((unsigned char)c);
+    const char *p = line.c_str() + 1;
+    for (int i = 0; i < nsym; i++)
+    {
+      long sc = 0;
+      int used = 0;
+      if (sscanf(p, "%ld%n", &sc, &used) < 1) return SWB_ERR_ARG;     // "Problem parsing score matrix file."
+      const int b = order[i];
+      if (a >= 0 && b >= 0 && a < 32 && b < 32) m[(a << 5) + b] = sc;
+      p += used;
+    }
+  }
+  return SWB_OK;
+}
+
+
 const SwbKaMatrix *ka_matrix(const char *name)
 {
   for (const SwbKaMatrix &k : swb_ka_protein)
@@ -90,43 +137,7 @@ int swb_matrix_builtin(const char *name, int64_t *m)
   return SWB_ERR_ARG;
 }
 
-// The text format of matrix files (matrices.cc:437-517): '#' comments; a line starting with a
-// blank lists the column symbols; every other line is "<row symbol> <score> <score> ...".  The
-// first symbol of a data line is the first index, i.e. entry [(row << 5) + column].
-int swb_matrix_parse(const char *text, int64_t *m)
-{
-  if (!text || !m) return SWB_ERR_ARG;
-  for (int i = 0; i < 1024; i++) m[i] = -1;
-  int order[4096], nsym = 0;
-  const char *s = text;
-  while (*s)
-  {
-    const char *e = strchr(s, '\n');
-    std::string line = e ? std::string(s, e - s) : std::string(s);
-    s = e ? e + 1 : s + line.size();
-    if (line.empty()) continue;
-    const char c = line[0];
-    if (c == '#' || c == '\n') continue;
-    if (c == ' ' || c == '\t')
-    {
-      for (size_t k = 1; k < line.size(); k++)
-        if (!strchr(" \t\n", line[k]) && nsym < 4096) order[nsym++] = aa_code((unsigned char)line[k]);
-      continue;
-    }
-    const int a = aa_code((unsigned char)c);
-    const char *p = line.c_str() + 1;
-    for (int i = 0; i < nsym; i++)
-    {
-      long sc = 0;
-      int used = 0;
-      if (sscanf(p, "%ld%n", &sc, &used) < 1) return SWB_ERR_ARG;     // "Problem parsing score matrix file."
-      const int b = order[i];
-      if (a >= 0 && b >= 0 && a < 32 && b < 32) m[(a << 5) + b] = sc;
-      p += used;
-    }
-  }
-  return SWB_OK;
-}
+int swb_matrix_parse(const char *text, int64_t *m) { return matrix_parse(text, m, aa_code); }
 
 int swb_matrix_read(const char *name_or_path, int64_t *m)
 {
@@ -140,6 +151,27 @@ int swb_matrix_read(const char *name_or_path, int64_t *m)
   while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
   fclose(f);
   return swb_matrix_parse(text.c_str(), m);
+}
+
+// -p 5 ("sound", matrices.cc:284-315, :366, :443): matrix files are read with the sound alphabet; the
+// built-in IDENTITY_5_1 scores 5 for equal symbols 1..31 and -1 otherwise.
+int swb_matrix_read_sound(const char *name_or_path, int64_t *m)
+{
+  if (!name_or_path || !m) return SWB_ERR_ARG;
+  if (strcasecmp(name_or_path, "identity_5_1") == 0)
+  {
+    for (int i = 0; i < 1024; i++) m[i] = -1;
+    for (int a = 1; a < 32; a++) m[(a << 5) + a] = 5;
+    return SWB_OK;
+  }
+  FILE *f = fopen(name_or_path, "r");
+  if (!f) return SWB_ERR_IO;
+  std::string text;
+  char buf[4096];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+  fclose(f);
+  return matrix_parse(text.c_str(), m, sound_code);
 }
 
 int swb_matrix_nucleotide(int64_t match, int64_t mismatch, int64_t *m)

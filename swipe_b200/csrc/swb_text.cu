@@ -37,6 +37,14 @@ int nt_of(int c)
   return p ? (int)(p - SYM_NT16) : -1;
 }
 
+// the "sound" alphabet of -p 5 (query.cc:31-49, :179): A-Z = 1..26, a-e = 27..31, case sensitive
+int sound_of(int c)
+{
+  if (c >= 'A' && c <= 'Z') return c - 'A' + 1;
+  if (c >= 'a' && c <= 'e') return c - 'a' + 27;
+  return -1;
+}
+
 inline int nt_complement(int c)                      // bit-reversed 4-bit code (query.cc:112)
 {
   return ((c & 1) << 3) | ((c & 2) << 1) | ((c & 4) >> 1) | ((c & 8) >> 3);
@@ -285,7 +293,7 @@ std::string seq_id(Ber &b, bool show_gis)
 
 extern "C" {
 
-// Query text -> symbol codes.  FASTA: an optional '>' description line, then sequence lines up to
+// Query text -> symbol codes (nucleotide: 0 = amino acids, 1 = nucleotides, 2 = the sound alphabet).  FASTA: an optional '>' description line, then sequence lines up to
 // the next '>' or the end.  Characters outside the alphabet are dropped (query.cc:317-325).
 // Returns the number of bytes of `text` consumed (the next record starts there), 0 at the end.
 int64_t swb_query_parse(const char *text, int64_t text_len, int nucleotide, uint8_t *seq,
@@ -315,7 +323,7 @@ int64_t swb_query_parse(const char *text, int64_t text_len, int nucleotide, uint
     const unsigned char c = (unsigned char)text[i];
     if (line_start && c == '>') break;
     line_start = c == '\n';
-    const int m = nucleotide ? nt_of(c) : aa_of(c);
+    const int m = nucleotide == 1 ? nt_of(c) : (nucleotide == 2 ? sound_of(c) : aa_of(c));
     if (m >= 0)
     {
       if (n < seq_cap) seq[n] = (uint8_t)m;

@@ -10,7 +10,7 @@
 //   align_chunk / hits_align .............. swipe.cc:339-414, hits.cc:546-623 (swb_search_end + swb_align)
 //   hits_show_plain / _xml / _tsv ......... hits.cc:647-1176, :1660-1945
 //   show_deflines ......................... asnparse.cc:889-971
-// Not carried over: -m 99, symtype 5 ("sound"), MPI.  `-a` (threads in the
+// Not carried over: -m 99 (ParalignXML), MPI.  `-a` (threads in the
 // reference) selects how many GPUs share the database, one host thread each.
 #include "../../include/swipe_b200.h"
 
@@ -70,6 +70,7 @@ struct Options
 
 const char SYM_AA[] = "-ABCDEFGHIKLMNPQRSTVWXYZU*OJ####";
 const char SYM_NT[] = "-acmgrsvtwyhkdbn################";
+const char SYM_SOUND[] = "-ABCDEFGHIJKLMNOPQRSTUVWXYZabcde";
 
 void usage(const char *prog)
 {
@@ -162,6 +163,7 @@ Options parse_args(int argc, char **argv)
         else if (!strcmp(optarg, "blastx")) o.symtype = 2;
         else if (!strcmp(optarg, "tblastn")) o.symtype = 3;
         else if (!strcmp(optarg, "tblastx")) o.symtype = 4;
+        else if (!strcmp(optarg, "sound")) o.symtype = 5;
         else o.symtype = atol(optarg);
         break;
       case 'q': o.mismatchscore = atol(optarg); break;
@@ -206,12 +208,18 @@ Options parse_args(int argc, char **argv)
     else if (o.gapopen == 0 && o.gapextend == 0)
       fatal("Unknown score matrix. Gap penalties must be specified (-G and -E).");
   }
+  else if (o.symtype == 5)
+  {
+    if (o.matrixname.empty()) o.matrixname = "IDENTITY_5_1";
+    if (o.gapopen == 0) o.gapopen = 15;
+    if (o.gapextend == 0) o.gapextend = 5;
+  }
   if (o.effdbsize < 0) fatal("Illegal effective db size specified");
   if (o.threads < 1 || o.threads > 256) fatal("Illegal number of threads specified");
   if (o.databasename.empty()) fatal("No database specified.");
   if (!(o.view == 0 || o.view == 7 || o.view == 8 || o.view == 9)) fatal("Illegal view type.");
   if (o.gapopen < 0 || o.gapextend < 0 || o.gapopen + o.gapextend < 1) fatal("Illegal gap penalties.");
-  if (o.symtype < 0 || o.symtype > 4) fatal("Illegal symbol type.");
+  if (o.symtype < 0 || o.symtype > 5) fatal("Illegal symbol type.");
   if (o.querystrands < 1 || o.querystrands > 3) fatal("Illegal query strands specified.");
   if (o.querystrands == 2 && (o.symtype == 1 || o.symtype == 3 || o.symtype == 4))
     fatal("Illegal strand specified for protein query.");
@@ -521,7 +529,7 @@ AlignView view_alignment(const Run &R, const Query &q, const Hit &h, bool xml_ma
 {
   const Options &o = R.o;
   AlignView v;
-  const char *sym = o.symtype == 0 ? SYM_NT : SYM_AA;
+  const char *sym = o.symtype == 0 ? SYM_NT : (o.symtype == 5 ? SYM_SOUND : SYM_AA);
   const std::vector<uint8_t> &qs = o.symtype == 0 ? q.nt[h.qstrand] : q.aa[3 * h.qstrand + h.qframe];
   int64_t qp = h.aqs, dp = h.ads;
   const char *p = h.ops.c_str();
@@ -772,7 +780,7 @@ void show_run_header(const Run &R, const Query &q)
 {
   const Options &o = R.o;
   static const char *const symtypes[] = {"Nucleotide", "Amino acid", "Translated query", "Translated database",
-                                         "Both translated"};
+                                         "Both translated", "Sound"};
   fprintf(out, "Database file:     %s\n", o.databasename.c_str());
   fprintf(out, "Database title:    %s\n", swb_blastdb_title(R.bdb));
   fprintf(out, "Database time:     %s\n", swb_blastdb_date(R.bdb));
@@ -849,9 +857,16 @@ void work(Run &R, Query &q)
   else if (o.symtype == 4) maxhits *= o.querystrands == 3 ? 36 : 18;
   R.keephits = std::min(R.keephits, maxhits);
   const int64_t qlen = (o.symtype == 0 || o.symtype == 2 || o.symtype == 4) ? (int64_t)q.nt[0].size() : (int64_t)q.aa[0].size();
-  check(swb_stats_init((int)o.symtype, o.matrixname.c_str(), o.matchscore, o.mismatchscore, o.gapopen,
-                       o.gapextend, qlen, R.masked_symcount, R.masked_nseq, o.effdbsize, o.minscore, o.maxscore, o.expect,
-                       o.minexpect, &R.st), "statistics");
+  if (o.symtype == 5)
+  {
+    memset(&R.st, 0, sizeof R.st);                    // no statistics for the sound alphabet (hits.cc:404)
+    R.st.score_threshold = o.minscore;
+    R.st.upper_threshold = o.maxscore;
+  }
+  else
+    check(swb_stats_init((int)o.symtype, o.matrixname.c_str(), o.matchscore, o.mismatchscore, o.gapopen,
+                         o.gapextend, qlen, R.masked_symcount, R.masked_nseq, o.effdbsize, o.minscore, o.maxscore,
+                         o.expect, o.minexpect, &R.st), "statistics");
   if (!R.st.available && o.view == 0)
     fprintf(out, "Statistical parameters are not available for the scoring system specified.\nBit scores and E-values will not be computed.\n\n");
   R.hits.clear();
@@ -929,7 +944,7 @@ int main(int argc, char **argv)
   if (o.dump)
   {
     // db_show_fasta (database.cc:1483-1537) for every sequence; needs no GPU
-    const char *sym = R.db_nt ? "-ACMGRSVTWYHKDBN################" : SYM_AA;
+    const char *sym = R.db_nt ? "-ACMGRSVTWYHKDBN################" : (o.symtype == 5 ? SYM_SOUND : SYM_AA);
     std::vector<uint8_t> seq;
     std::vector<char> buf(1 << 16);
     for (int64_t s = 0; s < R.nseq; s++)
@@ -990,7 +1005,8 @@ int main(int argc, char **argv)
   if (o.symtype == 0) swb_matrix_nucleotide(o.matchscore, o.mismatchscore, R.matrix);
   else
   {
-    const int rc = swb_matrix_read(o.matrixname.c_str(), R.matrix);
+    const int rc = o.symtype == 5 ? swb_matrix_read_sound(o.matrixname.c_str(), R.matrix)
+                                  : swb_matrix_read(o.matrixname.c_str(), R.matrix);
     if (rc == SWB_ERR_IO) fatal("Cannot open score matrix file.");
     if (rc != SWB_OK) fatal("Problem parsing score matrix file.");
   }
@@ -1053,7 +1069,8 @@ int main(int argc, char **argv)
     std::vector<uint8_t> seq(text.size() - at + 1);
     std::vector<char> descr(text.size() - at + 2);
     int64_t n = 0;
-    const int64_t used = swb_query_parse(text.data() + at, (int64_t)(text.size() - at), nt_query ? 1 : 0, seq.data(),
+    const int64_t used = swb_query_parse(text.data() + at, (int64_t)(text.size() - at),
+                                         nt_query ? 1 : (o.symtype == 5 ? 2 : 0), seq.data(),
                                          (int64_t)seq.size(), &n, descr.data(), (int64_t)descr.size());
     if (used <= 0) break;
     at += (size_t)used;

@@ -88,6 +88,23 @@ def build(tmp):
     open(os.path.join(tmp, "pm.pal"), "w").write(
         "TITLE masked subset\nDBLIST px\nOIDLIST mx.msk\nMEMB_BIT 1\nNSEQ %d\nLENGTH %d\nMAXOID %d\n" % (
             int(keep.sum()), int(sum(len(subs[i]) for i in range(nx) if keep[i])), nx - 1))
+    # -p 5: the "sound" alphabet (A-Z, a-e = codes 1..31) over a protein-type database
+    srng = np.random.default_rng(555)
+    sq = srng.integers(1, 32, size=120).astype(np.uint8)
+    ssubs = []
+    for i in range(40):
+        L = int(srng.integers(5, 200))
+        s_ = srng.integers(1, 32, size=L).astype(np.uint8)
+        if i % 4 == 0 and L > 30:
+            w = int(min(L, 60))
+            a = int(srng.integers(0, 120 - w))
+            s_[:w] = sq[a:a + w]
+            s_[w // 2] = (s_[w // 2] % 31) + 1
+        ssubs.append(s_)
+    blastdb.write_protein(os.path.join(tmp, "snd"), ssubs, title="sound db")
+    sound = "-ABCDEFGHIJKLMNOPQRSTUVWXYZabcde"
+    with open(os.path.join(tmp, "qs.fa"), "w") as f:
+        f.write(">soundquery\n%s\n" % "".join(sound[int(c)] for c in sq))
     # a custom matrix without statistics
     m = fixtures.asym_matrix().reshape(32, 32)
     letters = scoring.SYM_AA[1:28]
@@ -121,6 +138,8 @@ CASES = {
     "dump_protein": "-d px -N 1",
     "dump_protein_split": "-d px -N 2",
     "dump_nt": "-d n -p 0 -N 1",
+    "sound_plain": "-d snd -i qs.fa -p 5 -v 10 -b 3",
+    "sound_xml": "-d snd -i qs.fa -p sound -m 7 -v 12 -b 4 -G 8 -E 2",
     "nt_plain": "-d n -i qn.fa -p 0 -v 20 -b 10",
     "nt_tsv": "-d n -i qn.fa -p 0 -m 8 -b 60",
     "nt_plus_only": "-d n -i qn.fa -p 0 -S 1 -m 8 -b 30",
