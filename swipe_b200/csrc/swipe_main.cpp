@@ -10,7 +10,7 @@
 //   align_chunk / hits_align .............. swipe.cc:339-414, hits.cc:546-623 (swb_search_end + swb_align)
 //   hits_show_plain / _xml / _tsv ......... hits.cc:647-1176, :1660-1945
 //   show_deflines ......................... asnparse.cc:889-971
-// Not carried over: -m 99 (ParalignXML), MPI.  `-a` (threads in the
+// Not carried over: the MPI master / slave.  `-a` (threads in the
 // reference) selects how many GPUs share the database, one host thread each.
 #include "../../include/swipe_b200.h"
 
@@ -90,7 +90,7 @@ void usage(const char *prog)
   fprintf(out, "  -c, --min_score=NUM        minimum score of sequences to show (1)\n");
   fprintf(out, "  -u, --max_score=NUM        maximum score of sequences to show (inf.)\n");
   fprintf(out, "  -a, --num_threads=NUM      number of GPUs to use, one host thread each (1)\n");
-  fprintf(out, "  -m, --outfmt=NUM           output format [0,7-9=plain,xml,tsv,tsv+] (0)\n");
+  fprintf(out, "  -m, --outfmt=NUM           output format [0,7-9,99=plain,xml,tsv,tsv+,paralign xml] (0)\n");
   fprintf(out, "  -I, --show_gis             show gi numbers in results (no)\n");
   fprintf(out, "  -p, --symtype=NAME/NUM     symbol type/translation [0-4] (1)\n");
   fprintf(out, "  -S, --strand=NAME/NUM      query strands to search [1-3] (3)\n");
@@ -217,7 +217,7 @@ Options parse_args(int argc, char **argv)
   if (o.effdbsize < 0) fatal("Illegal effective db size specified");
   if (o.threads < 1 || o.threads > 256) fatal("Illegal number of threads specified");
   if (o.databasename.empty()) fatal("No database specified.");
-  if (!(o.view == 0 || o.view == 7 || o.view == 8 || o.view == 9)) fatal("Illegal view type.");
+  if (!(o.view == 0 || o.view == 7 || o.view == 8 || o.view == 9 || o.view == 99)) fatal("Illegal view type.");
   if (o.gapopen < 0 || o.gapextend < 0 || o.gapopen + o.gapextend < 1) fatal("Illegal gap penalties.");
   if (o.symtype < 0 || o.symtype > 5) fatal("Illegal symbol type.");
   if (o.querystrands < 1 || o.querystrands > 3) fatal("Illegal query strands specified.");
@@ -283,6 +283,9 @@ struct Run
   std::vector<Shard> shards;
   std::vector<Hit> hits;
   int64_t keephits = 0;
+  int64_t totalhits = 0, obvious = 0, compute7 = 0, queryno = 0;   // hits.cc:174-178, swipe.cc:111; totalhits is never reset
+  std::string started, completed;
+  double elapsed = 0, speed = 0;
   std::mutex mu;
 };
 
@@ -292,9 +295,12 @@ const std::vector<uint8_t> &query_variant(const Run &R, const Query &q, int qstr
   return q.aa[3 * qstrand + qframe];
 }
 
-void merge_hits(Run &R, std::vector<Hit> &local)
+void merge_hits(Run &R, std::vector<Hit> &local, int64_t tot, int64_t obv, int64_t computed)
 {
   std::lock_guard<std::mutex> g(R.mu);
+  R.totalhits += tot;
+  R.obvious += obv;
+  R.compute7 += computed;
   R.hits.insert(R.hits.end(), local.begin(), local.end());
   if ((int64_t)R.hits.size() > R.keephits)
   {
@@ -330,18 +336,25 @@ void search_shard(Run &R, const Query &q, Shard &S)
   const int qs2 = (o.symtype == 0 || o.symtype == 2 || o.symtype == 4) ? (o.querystrands == 1 ? 0 : 1) : 0;
   const int qf2 = (o.symtype == 2 || o.symtype == 4) ? 2 : 0;
   std::vector<Hit> local;
+  int64_t tot = 0, obv = 0, computed = 0;
   for (int qstrand = qs1; qstrand <= qs2; qstrand++)
     for (int qframe = 0; qframe <= qf2; qframe++)
     {
       const std::vector<uint8_t> &qv = query_variant(R, q, qstrand, qframe);
       check(swb_search(S.db, qv.data(), (int64_t)qv.size(), &sc, scores.data(), nullptr), "search");
       int64_t threshold = R.st.score_threshold;
+      const bool filtered = R.memb_bit != 0 || !R.taxids.empty();
+      if (!filtered) computed += nsub;
       for (int64_t j = 0; j < nsub; j++)
       {
         const int64_t s = scores[(size_t)j];
-        if (s < threshold || s > R.st.upper_threshold) continue;
+        if (filtered && o.view == 99 && included(R, S.first + j / unit)) computed++;   // only -m 99 reports it
+        if (s < R.st.score_threshold) continue;                // below the initial threshold: not even counted
         const int64_t seqno = S.first + j / unit;
         if (!included(R, seqno)) continue;
+        tot++;                                                 // hits_enter: score >= init_threshold (hits.cc:177)
+        if (s > R.st.upper_threshold) { obv++; continue; }     // hits.cc:174
+        if (s < threshold) continue;
         Hit h;
         h.seqno = seqno;
         h.score = s;
@@ -363,7 +376,7 @@ void search_shard(Run &R, const Query &q, Shard &S)
     }
   std::sort(local.begin(), local.end(), hit_before);
   if ((int64_t)local.size() > R.keephits) local.resize((size_t)R.keephits);
-  merge_hits(R, local);
+  merge_hits(R, local, tot, obv, computed);
 }
 
 // the subject as the aligner sees it (hits_align, hits.cc:562-571): strand / frame applied
@@ -746,6 +759,217 @@ void report_xml(Run &R, const Query &q, long showalignments, long showhits)
   fprintf(out, "  </hits>\n</result>\n");
 }
 
+// hits_show_xml_paralign (hits.cc:1215-1648)
+std::vector<std::string> deflines_of(const Run &R, const Hit &h)
+{
+  std::vector<char> buf(h.header.size() * 4 + 4096);
+  int64_t need = 0;
+  const uint8_t *tx = R.taxids.empty() ? nullptr : R.taxids.data();
+  int64_t n = swb_defline_text((const uint8_t *)h.header.data(), (int64_t)h.header.size(), 1, (int)R.o.show_taxid,
+                               R.memb_bit, tx, (int64_t)R.taxids.size(), buf.data(), (int64_t)buf.size(), &need);
+  if (n == SWB_ERR_RANGE)
+  {
+    buf.resize((size_t)need + 1);
+    n = swb_defline_text((const uint8_t *)h.header.data(), (int64_t)h.header.size(), 1, (int)R.o.show_taxid,
+                         R.memb_bit, tx, (int64_t)R.taxids.size(), buf.data(), (int64_t)buf.size(), &need);
+  }
+  if (n < 0) fatal("Error parsing binary ASN.1 in database sequence definition.");
+  std::vector<std::string> lines;
+  const std::string all(buf.data());
+  size_t p = 0;
+  for (int64_t k = 0; k < n; k++)
+  {
+    size_t e = all.find('\n', p);
+    if (e == std::string::npos) e = all.size();
+    lines.push_back(all.substr(p, e - p));
+    p = e + 1;
+  }
+  return lines;
+}
+
+// "gi|N|" prefix, link = text up to the first blank, rest = the title (hits_defline_split, hits.cc:1256-1287)
+void split_defline(const std::string &d, long *gi, std::string *link, std::string *rest)
+{
+  const char *p = d.c_str();
+  int len = 0;
+  *gi = 0;
+  if (sscanf(p, "gi|%ld%n", gi, &len) > 0) p += len;
+  if (*p == '|') p++;
+  const char *r = strchr(p, ' ');
+  link->clear();
+  if (r) { link->assign(p, r - p); *rest = r + 1; }
+  else *rest = p;
+}
+
+std::string anchor_of(const Run &R, const Hit &h)
+{
+  char a[200];
+  const long qn = (long)R.queryno, s = (long)h.seqno;
+  switch (R.o.symtype)
+  {
+    case 0: snprintf(a, sizeof a, "%ld_%ld__%c__+", qn, s, h.qstrand ? '-' : '+'); break;
+    case 2: snprintf(a, sizeof a, "%ld_%ld_%d_%c__", qn, s, h.qframe + 1, h.qstrand ? '-' : '+'); break;
+    case 3: snprintf(a, sizeof a, "%ld_%ld___%d_%c", qn, s, h.dframe + 1, h.dstrand ? '-' : '+'); break;
+    case 4: snprintf(a, sizeof a, "%ld_%ld_%d_%c_%d_%c", qn, s, h.qframe + 1, h.qstrand ? '-' : '+', h.dframe + 1, h.dstrand ? '-' : '+'); break;
+    default: snprintf(a, sizeof a, "%ld_%ld____", qn, s); break;
+  }
+  return a;
+}
+
+void report_paralign(Run &R, const Query &q, long showalignments, long showhits)
+{
+  const Options &o = R.o;
+  const bool aa_query = o.symtype == 1 || o.symtype == 3;
+  const std::vector<uint8_t> &qs = aa_query ? q.aa[0] : q.nt[0];
+  const char *qsym = (o.symtype == 1 || o.symtype == 3) ? SYM_AA : (o.symtype == 5 ? SYM_SOUND : SYM_NT);
+  const bool nt_db = o.symtype == 0 || o.symtype == 3 || o.symtype == 4;
+  const char *ncbidb = nt_db ? "Nucleotide" : "Protein", *ncbiopt = nt_db ? "GenBank" : "GenPept";
+  fprintf(out, "\t<paralignOutput>\n");
+  fprintf(out, "\t\t<queryInformation>\n");
+  fprintf(out, "\t\t\t<queryFilename>./%s</queryFilename>\n", o.queryname.c_str());
+  fprintf(out, "\t\t\t<querySequencetype>%s</querySequencetype>\n", aa_query ? "Amino Acid" : "Nucleotide");
+  fprintf(out, "\t\t\t<queryDescription>%s</queryDescription>\n", q.description.c_str());
+  fprintf(out, "\t\t\t<queryLength>%ld</queryLength>\n", (long)qs.size());
+  fprintf(out, "\t\t\t<querySequence>");
+  for (uint8_t c : qs) putc(qsym[c & 31], out);
+  fprintf(out, "</querySequence>\n\t\t</queryInformation>\n");
+  fprintf(out, "\t\t<databaseInformation>\n");
+  fprintf(out, "\t\t\t<databaseFilename>%s</databaseFilename>\n", o.databasename.c_str());
+  fprintf(out, "\t\t\t<databaseSequencetype>%s</databaseSequencetype>\n", nt_db ? "Nucleotide" : "Amino Acid");
+  fprintf(out, "\t\t\t<databaseDescription>%s</databaseDescription>\n", swb_blastdb_title(R.bdb));
+  fprintf(out, "\t\t\t<databaseVersion>%ld</databaseVersion>\n", 4L);
+  fprintf(out, "\t\t\t<databaseDate>%s</databaseDate>\n", swb_blastdb_date(R.bdb));
+  fprintf(out, "\t\t\t<residueCount>%ld</residueCount>\n", (long)R.masked_symcount);
+  fprintf(out, "\t\t\t<sequenceCount>%ld</sequenceCount>\n", (long)R.masked_nseq);
+  fprintf(out, "\t\t\t<longestSequenceLength>%ld</longestSequenceLength>\n", (long)R.longest);
+  fprintf(out, "\t\t</databaseInformation>\n");
+  static const char *const strands[] = {"", "Plus", "Minus", "Both"};
+  fprintf(out, "\t\t<options>\n\t\t\t<algorithm>Smith-Waterman</algorithm>\n");
+  if (o.symtype == 0 || o.symtype == 2 || o.symtype == 4)
+    fprintf(out, "\t\t\t<queryStrands>%s</queryStrands>\n", strands[o.querystrands]);
+  if (o.symtype == 0) fprintf(out, "\t\t\t<scoreMatrix>NT</scoreMatrix>\n");
+  else fprintf(out, "\t\t\t<scoreMatrix>%s</scoreMatrix>\n", o.matrixname.c_str());
+  fprintf(out, "\t\t\t<gapPenalties>\n");
+  fprintf(out, "\t\t\t\t<gapPenaltyOpen>%ld</gapPenaltyOpen>\n", o.gapopen);
+  fprintf(out, "\t\t\t\t<gapPenaltyExtension>%ld</gapPenaltyExtension>\n", o.gapextend);
+  for (const char *kind : {"ungapped", "gapped"})
+  {
+    fprintf(out, "\t\t\t\t<%s>\n", kind);
+    fprintf(out, "\t\t\t\t\t<%sLambda>%.4g</%sLambda>\n", kind, R.st.lambda, kind);
+    fprintf(out, "\t\t\t\t\t<%sKappa>%.4g</%sKappa>\n", kind, R.st.K, kind);
+    fprintf(out, "\t\t\t\t\t<%sEta>%.4g</%sEta>\n", kind, R.st.H, kind);
+    fprintf(out, "\t\t\t\t</%s>\n", kind);
+  }
+  fprintf(out, "\t\t\t</gapPenalties>\n");
+  fprintf(out, "\t\t\t<expectRange>\n\t\t\t\t<expectRangeFrom>%.2g</expectRangeFrom>\n", o.minexpect);
+  fprintf(out, "\t\t\t\t<expectRangeTo>%.2g</expectRangeTo>\n\t\t\t</expectRange>\n", o.expect);
+  fprintf(out, "\t\t\t<displayLimits>\n\t\t\t\t<hitLimit>%ld</hitLimit>\n", o.maxmatches);
+  fprintf(out, "\t\t\t\t<alignmentLimit>%ld</alignmentLimit>\n", o.alignments);
+  fprintf(out, "\t\t\t\t<subalignmentLimit>%ld</subalignmentLimit>\n\t\t\t</displayLimits>\n", 1L);
+  fprintf(out, "\t\t\t<threads>%ld</threads>\n\t\t</options>\n", o.threads);
+  fprintf(out, "\t\t\t<searchInformation>\n");
+  fprintf(out, "\t\t\t\t<searchStarted>%s</searchStarted>\n", R.started.c_str());
+  fprintf(out, "\t\t\t\t<searchCompleted>%s</searchCompleted>\n", R.completed.c_str());
+  fprintf(out, "\t\t\t\t<searchElapsedTime>%.2fs</searchElapsedTime>\n", R.elapsed);
+  fprintf(out, "\t\t\t\t<searchSpeed>%.3f GCUPS</searchSpeed>\n", R.speed / 1e9);
+  fprintf(out, "\t\t\t\t<searchSWAlignments>\n\t\t\t\t\t<SWAbsolute>%ld</SWAbsolute>\n", (long)R.compute7);
+  fprintf(out, "\t\t\t\t\t<SWPercent>100</SWPercent>\n\t\t\t\t</searchSWAlignments>\n\t\t\t</searchInformation>\n");
+  fprintf(out, "\t\t<resultInformation>\n\t\t\t<resultHits>\n");
+  fprintf(out, "\t\t\t\t<totalCount>%ld</totalCount>\n", (long)R.totalhits);
+  fprintf(out, "\t\t\t\t<obviousCount>%ld</obviousCount>\n", (long)R.obvious);
+  fprintf(out, "\t\t\t\t<shownCount>%ld</shownCount>\n\t\t\t</resultHits>\n", showhits);
+  fprintf(out, "\t\t\t<alignmentCount>%ld</alignmentCount>\n\t\t</resultInformation>\n", showalignments);
+  auto links = [&](const char *ver, const char *tabs, long gi, const std::string &link) {
+    if (gi)
+    {
+      fprintf(out, "%s<%sVersionLink>\n", tabs, ver);
+      fprintf(out, "%s\t<%sVersionLinkDestination>http://www.ncbi.nlm.nih.gov/entrez/query.fcgi?cmd=Retrieve&amp;db=%s&amp;list_uids=%ld&amp;dopt=%s</%sVersionLinkDestination>\n", tabs, ver, ncbidb, gi, ncbiopt, ver);
+      fprintf(out, "%s\t<%sVersionLinkText>gi|%ld</%sVersionLinkText>\n", tabs, ver, gi, ver);
+      fprintf(out, "%s</%sVersionLink>\n", tabs, ver);
+    }
+    fprintf(out, "%s<%sVersionLink>\n", tabs, ver);
+    fprintf(out, "%s\t<%sVersionLinkDestination>http://www.ncbi.nlm.nih.gov/entrez/query.fcgi?cmd=Search&amp;db=%s&amp;term=%s&amp;doptcmdl=%s</%sVersionLinkDestination>\n", tabs, ver, ncbidb, link.c_str(), ncbiopt, ver);
+    fprintf(out, "%s\t<%sVersionLinkText>%s</%sVersionLinkText>\n", tabs, ver, link.c_str(), ver);
+    fprintf(out, "%s</%sVersionLink>\n", tabs, ver);
+  };
+  fprintf(out, "\t\t<shortVersionHits>\n");
+  for (long i = 0; i < showhits; i++)
+  {
+    const Hit &h = R.hits[(size_t)i];
+    const std::vector<std::string> dl = deflines_of(R, h);
+    long gi = 0;
+    std::string link, title;
+    split_defline(dl.empty() ? std::string() : dl[0], &gi, &link, &title);
+    fprintf(out, "\t\t\t<shortVersionHit>\n\t\t\t\t<shortVersionAnchor>%s</shortVersionAnchor>\n", anchor_of(R, h).c_str());
+    links("short", "\t\t\t\t", gi, link);
+    fprintf(out, "\t\t\t\t<shortVersionName>%.35s</shortVersionName>\n", title.c_str());
+    if (o.symtype == 0) fprintf(out, "\t\t\t\t<shortVersionStrand>%c</shortVersionStrand>\n", h.qstrand ? '-' : '+');
+    else if (o.symtype == 2) fprintf(out, "\t\t\t\t<shortVersionFrame>%c%d</shortVersionFrame>\n", h.qstrand ? '-' : '+', h.qframe + 1);
+    else if (o.symtype == 3) fprintf(out, "\t\t\t\t<shortVersionFrame>%c%d</shortVersionFrame>\n", h.dstrand ? '-' : '+', h.dframe + 1);
+    else if (o.symtype == 4)
+      fprintf(out, "\t\t\t\t<shortVersionFrame>%c%d/%c%d</shortVersionFrame>\n", h.qstrand ? '-' : '+', h.qframe + 1, h.dstrand ? '-' : '+', h.dframe + 1);
+    fprintf(out, "\t\t\t\t<shortVersionScore>%ld</shortVersionScore>\n", (long)h.score);
+    fprintf(out, "\t\t\t\t<shortVersionEValue>%.2g</shortVersionEValue>\n\t\t\t</shortVersionHit>\n", swb_stats_evalue(&R.st, h.score));
+  }
+  fprintf(out, "\t\t</shortVersionHits>\n");
+  if (showalignments)
+  {
+    fprintf(out, "\t\t<longVersionHits>\n");
+    for (long i = 0; i < showalignments; i++)
+    {
+      const Hit &h = R.hits[(size_t)i];
+      fprintf(out, "\t\t\t<longVersionHit>\n\t\t\t\t<longVersionAnchor>%s</longVersionAnchor>\n", anchor_of(R, h).c_str());
+      fprintf(out, "\t\t\t\t<linkContainer>\n");
+      for (const std::string &d : deflines_of(R, h))
+      {
+        long gi = 0;
+        std::string link, title;
+        split_defline(d, &gi, &link, &title);
+        links("long", "\t\t\t\t\t", gi, link);
+        fprintf(out, "\t\t\t\t\t<longVersionName>%s</longVersionName>\n", title.c_str());
+      }
+      fprintf(out, "\t\t\t\t</linkContainer>\n");
+      if (o.symtype == 0) fprintf(out, "\t\t\t\t<databaseSequenceLength>%ld nt</databaseSequenceLength>\n", (long)h.dlen);
+      else if (o.symtype == 3 || o.symtype == 4) fprintf(out, "\t\t\t\t<databaseSequenceLength>%ld nt</databaseSequenceLength>\n", (long)h.dlennt);
+      else fprintf(out, "\t\t\t\t<databaseSequenceLength>%ld aa</databaseSequenceLength>\n", (long)h.dlen);
+      if (o.symtype == 0)
+        fprintf(out, "\t\t\t\t<alignmentMatchLocation>%s</alignmentMatchLocation>\n",
+                h.qstrand ? "Matches on complementary strands." : "Matches on same strands.");
+      else if (o.symtype >= 2 && o.symtype <= 4)
+      {
+        fprintf(out, "\t\t\t\t<longVersionFrames>\n");
+        if (o.symtype == 2 || o.symtype == 4)
+          fprintf(out, "\t\t\t\t\t<longVersionQueryFrame>\n\t\t\t\t\t\t<queryStrand>%c</queryStrand>\n\t\t\t\t\t\t<queryFrame>%d</queryFrame>\n\t\t\t\t\t</longVersionQueryFrame>\n",
+                  h.qstrand ? '-' : '+', h.qframe + 1);
+        if (o.symtype == 3 || o.symtype == 4)
+          fprintf(out, "\t\t\t\t\t<longVersionDatabaseFrame>\n\t\t\t\t\t\t<databaseStrand>%c</databaseStrand>\n\t\t\t\t\t\t<databaseFrame>%d</databaseFrame>\n\t\t\t\t\t</longVersionDatabaseFrame>\n",
+                  h.dstrand ? '-' : '+', h.dframe + 1);
+        fprintf(out, "\t\t\t\t</longVersionFrames>\n");
+      }
+      const AlignView v = view_alignment(R, q, h, true);
+      fprintf(out, "\t\t\t\t<alignment>\n\t\t\t\t\t<subalignment>\n");
+      fprintf(out, "\t\t\t\t\t\t<longVersionScore>%ld</longVersionScore>\n", (long)h.score);
+      fprintf(out, "\t\t\t\t\t\t<longVersionEValue>%.2g</longVersionEValue>\n", swb_stats_evalue(&R.st, h.score));
+      fprintf(out, "\t\t\t\t\t\t<identical>\n\t\t\t\t\t\t\t<identicalNominator>%ld</identicalNominator>\n\t\t\t\t\t\t\t<identicalDenominator>%ld</identicalDenominator>\n\t\t\t\t\t\t\t<identicalPercentage>%.1f</identicalPercentage>\n\t\t\t\t\t\t</identical>\n",
+              v.identities, v.aligned, 100.0 * v.identities / v.aligned);
+      if (o.symtype != 0)
+        fprintf(out, "\t\t\t\t\t\t<positive>\n\t\t\t\t\t\t\t<positiveNominator>%ld</positiveNominator>\n\t\t\t\t\t\t\t<positiveDenominator>%ld</positiveDenominator>\n\t\t\t\t\t\t\t<positivePercentage>%.1f</positivePercentage>\n\t\t\t\t\t\t</positive>\n",
+                v.positives, v.aligned, 100.0 * v.positives / v.aligned);
+      fprintf(out, "\t\t\t\t\t\t<indels>\n\t\t\t\t\t\t\t<indelsNominator>%ld</indelsNominator>\n\t\t\t\t\t\t\t<indelsDenominator>%ld</indelsDenominator>\n\t\t\t\t\t\t\t<indelsPercentage>%.1f</indelsPercentage>\n\t\t\t\t\t\t</indels>\n",
+              v.indels, v.aligned, 100.0 * v.indels / v.aligned);
+      fprintf(out, "\t\t\t\t\t\t<gaps>%ld</gaps>\n", v.gaps);
+      fprintf(out, "\t\t\t\t\t\t<alignmentQuery>\n\t\t\t\t\t\t\t<alignmentQueryStart>%ld</alignmentQueryStart>\n\t\t\t\t\t\t\t<alignmentQueryLine>%s</alignmentQueryLine>\n\t\t\t\t\t\t\t<alignmentQueryEnd>%ld</alignmentQueryEnd>\n\t\t\t\t\t\t</alignmentQuery>\n",
+              v.q_first, v.qline.c_str(), v.q_last);
+      fprintf(out, "\t\t\t\t\t\t<alignmentLine>%s</alignmentLine>\n", v.aline.c_str());
+      fprintf(out, "\t\t\t\t\t\t<alignmentDatabase>\n\t\t\t\t\t\t\t<alignmentDatabaseStart>%ld</alignmentDatabaseStart>\n\t\t\t\t\t\t\t<alignmentDatabaseLine>%s</alignmentDatabaseLine>\n\t\t\t\t\t\t\t<alignmentDatabaseEnd>%ld</alignmentDatabaseEnd>\n\t\t\t\t\t\t</alignmentDatabase>\n",
+              v.d_first, v.dline.c_str(), v.d_last);
+      fprintf(out, "\t\t\t\t\t</subalignment>\n\t\t\t\t</alignment>\n\t\t\t</longVersionHit>\n");
+    }
+    fprintf(out, "\t\t</longVersionHits>\n");
+  }
+  fprintf(out, "\t</paralignOutput>\n");
+}
+
 void report_tsv(Run &R, const Query &q, long showalignments, bool comments)
 {
   if (comments)
@@ -870,6 +1094,8 @@ void work(Run &R, Query &q)
   if (!R.st.available && o.view == 0)
     fprintf(out, "Statistical parameters are not available for the scoring system specified.\nBit scores and E-values will not be computed.\n\n");
   R.hits.clear();
+  R.obvious = 0;
+  R.compute7 = 0;
   if (o.view == 0)
   {
     fprintf(out, "Searching...");
@@ -887,9 +1113,7 @@ void work(Run &R, Query &q)
   if ((int64_t)R.hits.size() > R.keephits) R.hits.resize((size_t)R.keephits);
   const clock_t c2 = times(&t2);
   const time_t w2 = time(nullptr);
-  if (o.view == 0)
   {
-    fprintf(out, "...............................................done\n\n");
     char b1[40], b2[40];
     struct tm tmv;
     gmtime_r(&w1, &tmv); strftime(b1, sizeof b1, "%a, %e %b %Y %T UTC", &tmv);
@@ -901,18 +1125,25 @@ void work(Run &R, Query &q)
     else if (o.symtype == 2) speed *= (double)q.nt[0].size() * (o.querystrands == 3 ? 2 : 1);
     else if (o.symtype == 3) speed *= 2.0 * (double)q.aa[0].size();
     else speed *= 2.0 * (double)q.nt[0].size() * (o.querystrands == 3 ? 2 : 1);
-    fprintf(out, "Search started:    %s\n", b1);
-    fprintf(out, "Search completed:  %s\n", b2);
-    fprintf(out, "Elapsed:           %.2fs\n", elapsed);
-    fprintf(out, "Speed:             %.3f GCUPS\n", speed / elapsed / 1e9);
-    fprintf(out, "\n");
+    R.started = b1; R.completed = b2; R.elapsed = elapsed; R.speed = speed / elapsed;
+    if (o.view == 0)
+    {
+      fprintf(out, "...............................................done\n\n");
+      fprintf(out, "Search started:    %s\n", b1);
+      fprintf(out, "Search completed:  %s\n", b2);
+      fprintf(out, "Elapsed:           %.2fs\n", elapsed);
+      fprintf(out, "Speed:             %.3f GCUPS\n", speed / elapsed / 1e9);
+      fprintf(out, "\n");
+    }
   }
   align_hits(R, q);
   const long showhits = (long)std::min<int64_t>((int64_t)R.hits.size(), o.maxmatches);
   const long showalignments = (long)std::min<int64_t>((int64_t)R.hits.size(), o.alignments);
   if (o.view == 0) report_plain(R, q, showalignments, showhits);
   else if (o.view == 7) report_xml(R, q, showalignments, showhits);
+  else if (o.view == 99) report_paralign(R, q, showalignments, showhits);
   else report_tsv(R, q, showalignments, o.view == 9);
+  R.queryno++;
 }
 
 }  // namespace
@@ -1062,6 +1293,17 @@ int main(int argc, char **argv)
                  "SWIPE: T. Rognes (2011) BMC Bioinformatics, 12:221.\n\n", SWB_CLI_VERSION);
   else if (o.view == 7)
     fprintf(out, "<?xml version=\"1.0\"?>\n");
+  else if (o.view == 99)
+  {
+    fprintf(out, "<?xml version=\"1.0\"?>\n");
+    fprintf(out, "<ParalignXML xmlns:xsi=\"http://www.w3.org/2001/XMLSchema-instance\" xsi:noNamespaceSchemaLocation=\"http://www.paralign.org/ParalignXML.xsd\">\n");
+    fprintf(out, "\t<programInformation>\n\t\t<programName>swipe</programName>\n");
+    fprintf(out, "\t\t<programVersion>SWIPE-B200 %s</programVersion>\n", SWB_CLI_VERSION);
+    fprintf(out, "\t\t<programDescription>Smith-Waterman database searches with inter-sequence SIMD parallelisation</programDescription>\n");
+    fprintf(out, "\t\t<articleReferences>\n\t\t\t<reference>T. Rognes (2011) Faster Smith-Waterman database searches with inter-sequence SIMD parallelisation, BMC Bioinformatics, 12:221.</reference>\n\t\t</articleReferences>\n");
+    fprintf(out, "\t\t<license>SWIPE is available under the GNU Affero General Public License, version 3</license>\n");
+    fprintf(out, "\t</programInformation>\n");
+  }
   const bool nt_query = o.symtype == 0 || o.symtype == 2 || o.symtype == 4;
   size_t at = 0;
   while (at < text.size())
@@ -1080,6 +1322,7 @@ int main(int argc, char **argv)
     build_query(R, q, seq);
     work(R, q);
   }
+  if (o.view == 99) fprintf(out, "</ParalignXML>\n");
   for (Shard &S : R.shards) swb_db_close(S.db);
   swb_blastdb_close(R.bdb);
   if (o.outfile) fclose(out);

@@ -138,6 +138,10 @@ CASES = {
     "dump_protein": "-d px -N 1",
     "dump_protein_split": "-d px -N 2",
     "dump_nt": "-d n -p 0 -N 1",
+    "paralign_protein": "-d px -i q2.fa -m 99 -e 1e30 -v 6 -b 2",
+    "paralign_nt": "-d n -i qn.fa -p 0 -m 99 -v 5 -b 2",
+    "paralign_tblastx": "-d t -i qx.fa -p 4 -m 99 -v 4 -b 2 -e 100",
+    "paralign_taxid_masked": "-d pm -i q.fa -m 99 -x tax.txt -e 1e30 -v 5 -b 1",
     "sound_plain": "-d snd -i qs.fa -p 5 -v 10 -b 3",
     "sound_xml": "-d snd -i qs.fa -p sound -m 7 -v 12 -b 4 -G 8 -E 2",
     "nt_plain": "-d n -i qn.fa -p 0 -v 20 -b 10",
@@ -155,7 +159,8 @@ CASES = {
 
 # lines that legitimately differ: program banner, wall-clock lines, the thread count's meaning
 DROP = re.compile(r"^(SWIPE|Reference:|with inter-sequence|Score-only Smith-Waterman|SWIPE:|# SWIPE|"
-                  r"Search started:|Search completed:|Elapsed:|Speed:|Threads:)")
+                  r"Search started:|Search completed:|Elapsed:|Speed:|Threads:|"
+                  r"\s*<(searchStarted|searchCompleted|searchElapsedTime|searchSpeed|programVersion|threads)>)")
 
 
 def normalise(text):
