@@ -191,7 +191,9 @@ def main():
                           "(BASELINE configs[1])",
               "qlen": args.qlen, "nseq_per_gpu": args.nseq, "gap_open": GAP_OPEN,
               "gap_extend": GAP_EXTEND, "matrix": "BLOSUM62", "sharding": "by sequence, no collective",
-              "l2": "inputs (1.8 GB/shard) larger than L2"}
+              "l2": "inputs (1.8 GB/shard) larger than L2",
+              "lanes": "two int16 lanes per 32-bit register: DPX s16x2 max / add-max, adds as fp16x2 on integer "
+                       "bit patterns (exact to 2047), re-queue to plain int16 lanes and then 32/64-bit cells"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -213,7 +215,7 @@ def main():
         line = {"metric": "GCUPS", "value": v, "unit": "GCUPS", "impl": "reference",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "int8/int16 SSE lanes (reference search7/search16)",
+                "vs_baseline": None, "dtype": "int8",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": cores, "kind": kind,
                                  "sample": desc},
@@ -369,7 +371,7 @@ def main():
         line = {
             "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int16x2 DPX lanes + fp16x2-pattern adds (exact integers)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16",
             "data": "synthetic", "config": config, "clocks": clocks,
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
