@@ -307,7 +307,7 @@ int prepare_tables(Tables &t, const unsigned char *query, long long qlen, const 
   t.limit7 = 128 - t.hi;
   t.limit16 = 65536 - t.hi;
   const long long q = sc->gap_open_extend, r = sc->gap_extend;
-  t.narrow_ok = t.nq <= 30 && t.hi <= 1024 && t.lo >= -1024 && q >= 0 && q <= 8192 && r >= 0 &&
+  t.narrow_ok = t.nq <= 32 && t.hi <= 1024 && t.lo >= -1024 && q >= 0 && q <= 8192 && r >= 0 &&
                 r <= 8192;
   t.hybrid_ok = t.narrow_ok && t.hi <= 256 && t.lo >= -1023 && q <= 1023 && r <= 1023;
   t.m16.assign(SWB_M16_BYTES / sizeof(short), 0);

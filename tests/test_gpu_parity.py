@@ -151,14 +151,24 @@ def test_asymmetric_matrix_and_all_symbols(oracle):
             _check(db, q, Scoring(m, 7, 2), oracle, residues, offsets, "asym")
 
 
-def test_many_query_symbols_fall_back_to_wide(oracle):
-    """More than 30 distinct query codes cannot use the packed table rows."""
-    q = np.arange(32, dtype=np.uint8)
+def test_all_32_query_symbols(oracle):
+    """A query using every one of the 32 symbol codes (the sound alphabet of -p 5 uses 31): the packed
+    kernel's per-block tables hold up to 32 symbol rows, in every shape."""
     rng = np.random.default_rng(2)
-    subs = [rng.integers(0, 32, size=int(rng.integers(1, 80))).astype(np.uint8) for _ in range(50)]
+    q = np.concatenate([np.arange(32), rng.integers(0, 32, size=300)]).astype(np.uint8)
+    subs = [rng.integers(0, 32, size=int(rng.integers(1, 400))).astype(np.uint8) for _ in range(300)]
+    subs.append(q[10:200].copy())
     residues, offsets = fixtures.pack(subs)
+    sound = np.full((32, 32), -1, dtype=np.int64)
+    for a in range(1, 32):
+        sound[a, a] = 5
     with Database(residues, offsets) as db:
-        _check(db, q, Scoring(fixtures.asym_matrix(), 3, 1), oracle, residues, offsets, "32 symbols")
+        for shape in ((0, 0, -1), (8, 13, 1), (16, 24, 0), (32, 12, 1)):
+            db.set_shape(*shape)
+            _, c = _check(db, q, Scoring(fixtures.asym_matrix(), 3, 1), oracle, residues, offsets, "32 symbols %s" % (shape,))
+            assert c["gpu_narrow"] + c["gpu_middle"] == len(subs)
+        db.set_shape(0, 0, -1)
+        _check(db, q, Scoring(sound.reshape(-1), 15, 5), oracle, residues, offsets, "sound identity")
 
 
 def test_nucleotide_both_strands(oracle):
