@@ -97,6 +97,9 @@ int swb_host_free(void *ptr);
 /* Device buffers of closed handles are kept for reuse (cudaMalloc/cudaFree synchronise the device);
  * swb_trim() returns them to the driver. */
 int swb_trim(void);
+/* Budget of that cache in bytes PER DEVICE (default 8 GiB, or SWB_CACHE_MB from the environment);
+ * a buffer that would push a device's cached total beyond it is freed at once.  0 = no caching. */
+int swb_set_cache_limit(int64_t bytes_per_device);
 
 /* ---- database shard ----------------------------------------------------------------------
  * Replaces db_mapsequences + the db_getsequence pulls the reference kernels make while they
@@ -122,6 +125,9 @@ int swb_db_open(int device, const uint8_t *residues, const int64_t *offsets, int
 int swb_db_open_async(int device, const uint8_t *residues, const int64_t *offsets, int64_t nseq,
                       int trailing, void *stream, swb_db **db);
 int swb_db_wait(swb_db *db);
+/* Closing releases the handle; its device buffers go to the reuse cache described at swb_trim()
+ * (up to the per-device budget), so device memory is not necessarily returned to the driver until
+ * swb_trim() is called.                                                                          */
 int swb_db_close(swb_db *db);
 int swb_db_info(const swb_db *db, int64_t *nseq, int64_t *total_residues, int64_t *longest);
 
@@ -185,6 +191,28 @@ int swb_search(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring
  */
 int swb_search_list(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
                     const int64_t *seqnos, int64_t n, int64_t *scores, swb_counters *counters);
+
+/* swb_search_hits: swb_search followed by the sink's admission rule ON THE DEVICE, so that only
+ * the hits the reference would have kept cross the bus.  hits_enter (hits.cc:163-222) never stores
+ * a score below scorethreshold or above upperscorethreshold (:180-184) and, once `keep` hits are
+ * held, raises the threshold to the last kept score (:218-219); the final list is therefore the
+ * best `keep` admissible subjects ordered by score descending, then sequence number descending
+ * (:188-191).  This call returns exactly that list for the shard: out_seqno[k] = seqno_base +
+ * subject number, out_score[k], k < *nhits <= keep; *totalhits = subjects with score >= min_score,
+ * *obvious = subjects with score > upper_score (hits.cc:174-178).  Device work: a histogram of the
+ * admissible scores, the bin of the keep-th score, a compaction of everything at or above it, a
+ * radix sort of those candidates; keep * 16 bytes come back instead of 8 bytes per subject.
+ * The per-shard lists of several GPUs are combined with swb_hits_merge.                          */
+int swb_search_hits(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
+                    int64_t seqno_base, int64_t keep, int64_t min_score, int64_t upper_score,
+                    int64_t *out_seqno, int64_t *out_score, int64_t *nhits, int64_t *totalhits,
+                    int64_t *obvious, swb_counters *counters);
+
+/* Merges hit lists that are each in the sink's order (what swb_search_hits returns) into the best
+ * `keep` overall -- the master's merge of the reference's MPI build (swipe.cc:1957-1974) and the
+ * host-side step of a multi-GPU search.  Returns the number of hits written or a negative status. */
+int64_t swb_hits_merge(int nlists, const int64_t *const *seqnos, const int64_t *const *scores,
+                       const int64_t *n, int64_t keep, int64_t *out_seqno, int64_t *out_score);
 
 /* swb_search_end: search16s's contract (swipe.h:237-249, search16s.cc:390-405, called from
  * align_chunk swipe.cc:381-393): exact score plus the alignment end -- bestpos = first subject

@@ -21,7 +21,8 @@ EXPORTS = ["swb_abi_version", "swb_align", "swb_blastdb_close", "swb_blastdb_dat
            "swb_host_alloc", "swb_host_free", "swb_last_cuda_error", "swb_matrix_builtin",
            "swb_matrix_limits", "swb_matrix_nucleotide", "swb_matrix_parse", "swb_matrix_read",
            "swb_matrix_read_sound", "swb_query_parse", "swb_revcomp", "swb_search",
-           "swb_search_end", "swb_search_list", "swb_set_mode", "swb_set_shape",
+           "swb_search_end", "swb_search_hits", "swb_search_list", "swb_set_cache_limit",
+           "swb_hits_merge", "swb_set_mode", "swb_set_shape",
            "swb_stats_bits", "swb_stats_default_gaps", "swb_stats_evalue", "swb_stats_init",
            "swb_stats_length_adjustment", "swb_stats_params", "swb_stats_params_nt", "swb_strerror",
            "swb_topk_merge", "swb_translate", "swb_translate_table", "swb_trim"]
@@ -83,6 +84,15 @@ def load_library():
                                     C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Counters)]
     lib.swb_search_end.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Scoring),
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.swb_search_hits.restype = C.c_int
+    lib.swb_search_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Scoring), C.c_int64,
+                                    C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, p64, p64,
+                                    p64, C.POINTER(Counters)]
+    lib.swb_hits_merge.restype = C.c_int64
+    lib.swb_hits_merge.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), p64, C.c_int64,
+                                   C.c_void_p, C.c_void_p]
+    lib.swb_set_cache_limit.restype = C.c_int
+    lib.swb_set_cache_limit.argtypes = [C.c_int64]
     lib.swb_topk_merge.restype = C.c_int64
     lib.swb_topk_merge.argtypes = [C.c_int, C.POINTER(C.c_void_p), p64, p64, C.c_int64, C.c_int64,
                                    C.c_int64, C.c_void_p, C.c_void_p, p64, p64]
@@ -319,6 +329,25 @@ class Database:
         self.last_counters = ctr.as_dict()
         return scores
 
+    def search_hits(self, query, scoring, keep, min_score=1, upper_score=2 ** 62, seqno_base=0):
+        """swb_search_hits: the best `keep` admissible subjects, selected on the device, in the
+        sink's order.  Returns (seqnos, scores, totalhits, obvious)."""
+        q = _u8(query)
+        keep = int(keep)
+        if getattr(self, "_hit_keep", -1) < keep:
+            self._hit_seq = np.empty(max(keep, 1), dtype=np.int64)
+            self._hit_sc = np.empty(max(keep, 1), dtype=np.int64)
+            self._hit_keep = keep
+        k, tot, obv = C.c_int64(), C.c_int64(), C.c_int64()
+        ctr = Counters()
+        sc = scoring._c()
+        _check(self._lib.swb_search_hits(self._h, q.ctypes.data, q.size, C.byref(sc), int(seqno_base),
+                                         keep, int(min_score), int(upper_score),
+                                         self._hit_seq.ctypes.data, self._hit_sc.ctypes.data,
+                                         C.byref(k), C.byref(tot), C.byref(obv), C.byref(ctr)))
+        self.last_counters = ctr.as_dict()
+        return self._hit_seq[:k.value].copy(), self._hit_sc[:k.value].copy(), tot.value, obv.value
+
     def search_list(self, query, scoring, seqnos):
         """seqnos: plain sequence numbers; coded (seqno << 3) for the ABI as the reference does."""
         q = _u8(query)
@@ -379,3 +408,24 @@ def topk_merge(score_arrays, seqno_bases, keep, min_score=0, upper_score=2 ** 62
     if k < 0:
         _check(int(k))
     return out_seq[:k].copy(), out_sc[:k].copy(), tot.value, obv.value
+
+
+def hits_merge(lists, keep):
+    """swb_hits_merge over [(seqnos, scores), ...], each already in the sink's order."""
+    lib = load_library()
+    seqs = [np.ascontiguousarray(a, dtype=np.int64) for a, _ in lists]
+    scs = [np.ascontiguousarray(b, dtype=np.int64) for _, b in lists]
+    n = len(seqs)
+    p1 = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in seqs])
+    p2 = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in scs])
+    ns = (C.c_int64 * max(n, 1))(*[a.size for a in seqs])
+    out_seq = np.empty(max(keep, 1), dtype=np.int64)
+    out_sc = np.empty(max(keep, 1), dtype=np.int64)
+    k = lib.swb_hits_merge(n, p1, p2, ns, int(keep), out_seq.ctypes.data, out_sc.ctypes.data)
+    if k < 0:
+        _check(int(k))
+    return out_seq[:k].copy(), out_sc[:k].copy()
+
+
+def set_cache_limit(nbytes):
+    _check(load_library().swb_set_cache_limit(int(nbytes)))

@@ -715,6 +715,115 @@ __global__ void swb_requeue_codes_kernel(const long long *requeue, long long n, 
   codes[k] = list ? (list[pos] & ~7ll) : (pos << 3);
 }
 
+// ---- the sink on the device: hits_enter's admission rule (hits.cc:163-222) over the final scores ---
+// The reference never materialises scores outside [scorethreshold, upperscorethreshold] and, once
+// its list is full, tightens the threshold to the K-th score (hits.cc:180-184, :218-219).  Here:
+// (1) one pass builds a histogram of the admissible scores (plus the width bookkeeping and the
+// totalhits / obvious counts), (2) one block finds the K-th score's bin, (3) one pass appends
+// (score << 32 | subject) of everything at or above it to a candidate list, which is then sorted
+// descending -- score first, subject number second, the reference's order -- and cut to K.
+#define SWB_HIST_BINS 4096     // scores >= 4095 share the last bin (the cut is then conservative)
+
+// counts: [0..2] subjects the reference's 7 / 16 / 63-bit pass would have kept, [3] totalhits
+// (score >= min_score), [4] obvious (score > upper)
+__global__ void __launch_bounds__(256) swb_hist_kernel(const long long *scores, long long n,
+                                                        long long limit7, long long limit16,
+                                                        long long min_score, long long upper,
+                                                        unsigned long long *counts, unsigned *hist)
+{
+  __shared__ unsigned sh[SWB_HIST_BINS];
+  __shared__ unsigned long long cnt[5];
+  for (int i = threadIdx.x; i < SWB_HIST_BINS; i += blockDim.x) sh[i] = 0;
+  if (threadIdx.x < 5) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned w7 = 0, w16 = 0, w63 = 0, tot = 0, obv = 0;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x)
+  {
+    const long long v = scores[k];
+    if (v < limit7) w7++; else if (v < limit16) w16++; else w63++;
+    tot += v >= min_score;
+    obv += v > upper;
+    if (v >= min_score && v <= upper)
+      atomicAdd(&sh[v < 0 ? 0 : (v > SWB_HIST_BINS - 1 ? SWB_HIST_BINS - 1 : (int)v)], 1u);
+  }
+  w7 = __reduce_add_sync(0xffffffffu, w7);
+  w16 = __reduce_add_sync(0xffffffffu, w16);
+  w63 = __reduce_add_sync(0xffffffffu, w63);
+  tot = __reduce_add_sync(0xffffffffu, tot);
+  obv = __reduce_add_sync(0xffffffffu, obv);
+  if ((threadIdx.x & 31) == 0)
+  {
+    if (w7) atomicAdd(&cnt[0], (unsigned long long)w7);
+    if (w16) atomicAdd(&cnt[1], (unsigned long long)w16);
+    if (w63) atomicAdd(&cnt[2], (unsigned long long)w63);
+    if (tot) atomicAdd(&cnt[3], (unsigned long long)tot);
+    if (obv) atomicAdd(&cnt[4], (unsigned long long)obv);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SWB_HIST_BINS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+  if (threadIdx.x < 5 && cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], cnt[threadIdx.x]);
+}
+
+// one block of 1024 threads: cut[0] = the highest bin c with count(bin >= c) >= keep (0 when fewer
+// than keep scores are admissible): everything in bins >= c is a candidate
+__global__ void __launch_bounds__(1024) swb_cut_kernel(const unsigned *hist, long long keep, unsigned *cut)
+{
+  __shared__ unsigned long long part[1024];
+  const int t = threadIdx.x;
+  constexpr int PER = SWB_HIST_BINS / 1024;
+  unsigned long long mine = 0;                    // thread t owns bins top-down: BINS-1 - PER*t - j
+  for (int j = 0; j < PER; j++) mine += hist[SWB_HIST_BINS - 1 - (PER * t + j)];
+  part[t] = mine;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1)              // inclusive scan (Hillis-Steele; 10 rounds)
+  {
+    const unsigned long long add = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += add;
+    __syncthreads();
+  }
+  const unsigned long long before = part[t] - mine;
+  if (t == 0) cut[0] = 0;
+  __syncthreads();
+  if (keep > 0 && before < (unsigned long long)keep && part[t] >= (unsigned long long)keep)
+  {
+    unsigned long long acc = before;
+    for (int j = 0; j < PER; j++)
+    {
+      const int bin = SWB_HIST_BINS - 1 - (PER * t + j);
+      acc += hist[bin];
+      if (acc >= (unsigned long long)keep) { cut[0] = (unsigned)bin; break; }
+    }
+  }
+}
+
+// cand[slot] = score << 32 | subject for every admissible score whose bin is >= cut[0]
+__global__ void __launch_bounds__(256) swb_compact_kernel(const long long *scores, long long n,
+                                                           long long min_score, long long upper,
+                                                           const unsigned *cut, unsigned long long *cand,
+                                                           unsigned long long *ncand)
+{
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long c = (long long)cut[0];
+  bool take = false;
+  long long v = 0;
+  if (k < n)
+  {
+    v = scores[k];
+    const long long bin = v > SWB_HIST_BINS - 1 ? SWB_HIST_BINS - 1 : v;
+    take = v >= min_score && v <= upper && bin >= c;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  if (!m) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(ncand, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (take) cand[base + __popc(m & ((1u << lane) - 1))] = ((unsigned long long)v << 32) | (unsigned long long)k;
+}
+
 // reference-width bookkeeping: which of the reference's passes would have kept each score
 __global__ void swb_widthcount_kernel(const long long *scores, long long n, long long limit7,
                                       long long limit16, unsigned long long *counts)

@@ -59,7 +59,17 @@ struct DevCache
 {
   std::mutex mu;
   std::multimap<std::pair<int, size_t>, void *> free_blocks;
-  size_t cached = 0;
+  size_t cached[64] = {0};        // bytes held per device
+  long long limit = -1;           // per-device budget; -1 = not set yet (SWB_CACHE_MB or 8 GiB)
+  size_t budget()
+  {
+    if (limit < 0)
+    {
+      const char *env = getenv("SWB_CACHE_MB");
+      limit = env ? std::max<long long>(0, atoll(env)) << 20 : (long long)8 << 30;
+    }
+    return (size_t)limit;
+  }
   static size_t round_up(size_t bytes)
   {
     size_t b = bytes < 512 ? 512 : bytes;
@@ -75,17 +85,17 @@ struct DevCache
     if (it == free_blocks.end()) return nullptr;
     void *p = it->second;
     free_blocks.erase(it);
-    cached -= rounded;
+    cached[dev & 63] -= rounded;
     return p;
   }
   void give(int dev, size_t rounded, void *p)
   {
     {
       std::lock_guard<std::mutex> g(mu);
-      if (cached + rounded <= (size_t)48 << 30)
+      if (cached[dev & 63] + rounded <= budget())
       {
         free_blocks.emplace(std::make_pair(dev, rounded), p);
-        cached += rounded;
+        cached[dev & 63] += rounded;
         return;
       }
     }
@@ -94,9 +104,16 @@ struct DevCache
   void trim()
   {
     std::lock_guard<std::mutex> g(mu);
-    for (auto &kv : free_blocks) cudaFree(kv.second);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &kv : free_blocks)
+    {
+      cudaSetDevice(kv.first.first);
+      cudaFree(kv.second);
+    }
+    cudaSetDevice(cur);
     free_blocks.clear();
-    cached = 0;
+    for (size_t &c : cached) c = 0;
   }
 };
 DevCache g_cache;
@@ -170,6 +187,14 @@ struct Layout
 
 struct Shape { int G, R; };
 
+// swb_search_hits: the sink's admission rule applied on the device (see swb_hist_kernel)
+struct HitsReq
+{
+  long long seqno_base = 0, keep = 0, min_score = 0, upper = 0;
+  long long *out_seqno = nullptr, *out_score = nullptr;
+  long long nhits = 0, totalhits = 0, obvious = 0;
+};
+
 }  // namespace
 
 struct swb_db
@@ -209,6 +234,10 @@ struct swb_db
   DevBuf<unsigned char> he;
   DevBuf<uint4> bndH, bndF;
   DevBuf<ScanSeg> segs;           // chunk table of a merged (whole-shard) scan launch
+  DevBuf<unsigned> hist;          // [SWB_HIST_BINS] admissible scores, [SWB_HIST_BINS] = the cut bin
+  DevBuf<unsigned long long> cand, cand_sorted;   // score << 32 | subject of the candidates
+  DevBuf<unsigned char> sort_tmp;
+  std::vector<unsigned long long> h_cand;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_group[2] = {nullptr, nullptr};   // completion of the last two scan launches
   double upload_ms = 0, layout_ms = 0;
@@ -256,10 +285,24 @@ int build_layout(swb_db *db, Layout &L, const long long *d_list, long long first
   tb = L.cub_tmp.cap;
   SWB_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp.p, tb, L.nblk.p, L.pairblk.p,
                                          (int)(L.npairs + 1), st));
-  // upper bound of the block total without a round trip: sum(max len) <= total residues
-  const long long bound_res = std::min<long long>(res_bound, n * db->longest);
-  L.res_bytes = bound_res;
-  L.cap_blocks = (bound_res + 3 * L.npairs) / 4 + 1;
+  if (d_list)
+  {
+    // a caller's list may name a subject any number of times, so the residues of the shard do not
+    // bound it: read the exact block total back (the list paths synchronise anyway)
+    long long total_blocks = 0;
+    SWB_CUDA(cudaMemcpyAsync(&total_blocks, L.pairblk.p + L.npairs, sizeof total_blocks,
+                             cudaMemcpyDeviceToHost, st));
+    SWB_CUDA(cudaStreamSynchronize(st));
+    L.res_bytes = 4 * total_blocks;
+    L.cap_blocks = total_blocks + 1;
+  }
+  else
+  {
+    // upper bound of the block total without a round trip: sum(max len) <= total residues
+    const long long bound_res = std::min<long long>(res_bound, n * db->longest);
+    L.res_bytes = bound_res;
+    L.cap_blocks = (bound_res + 3 * L.npairs) / 4 + 1;
+  }
   SWB_TRY(L.blocks.reserve((size_t)L.cap_blocks));
   const long long threads = L.npairs * 32;
   swb_fill_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(
@@ -448,10 +491,10 @@ int check_args(const swb_db *db, const unsigned char *query, long long qlen, con
 // The cascade over n subjects (the whole shard when h_list == NULL).
 int search_impl(swb_db *db, const unsigned char *query, long long qlen, const swb_scoring *sc,
                 const long long *h_list, long long n, long long *scores, long long *bestpos,
-                long long *bestq, swb_counters *ctr)
+                long long *bestq, swb_counters *ctr, HitsReq *hits = nullptr)
 {
   SWB_TRY(check_args(db, query, qlen, sc));
-  if (n < 0 || (n > 0 && !scores)) return SWB_ERR_ARG;
+  if (n < 0 || (n > 0 && !scores && !hits)) return SWB_ERR_ARG;
   SWB_CUDA(cudaSetDevice(db->device));
   cudaStream_t st = db->stream;
   const bool want_end = bestpos != nullptr;
@@ -493,7 +536,8 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
   SWB_TRY(prepare_tables(tb, query, qlen, sc, mode, (int)rows_padded));
   const long long maxcell = std::max<long long>(tb.hi, 0) * std::min<long long>(qlen, db->longest);
   const bool use64 = maxcell + sc->gap_open_extend + 65536 > 0x7fffffffLL ||
-                     sc->gap_open_extend > 0x3fffffff || tb.lo < -0x3fffffff;
+                     sc->gap_open_extend > 0x3fffffff || sc->gap_extend > 0x3fffffff ||
+                     tb.lo < -0x3fffffff;
 
   SWB_TRY(db->scores.reserve((size_t)std::max<long long>(n, 1)));
   SWB_TRY(db->counters.reserve(8));
@@ -520,12 +564,13 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
 
   long long nrequeue = 0;
   const bool narrow = !want_end && db->mode == 0 && tb.narrow_ok && qlen > 0 && n > 0;
-  if (n == 0)
+  if (n == 0 || qlen == 0)
   {
-  }
-  else if (qlen == 0)
-  {
-    SWB_CUDA(cudaMemsetAsync(db->scores.p, 0, (size_t)n * sizeof(long long), st));
+    // nothing to scan, but the open's copies may still be reading the caller's buffers: the
+    // contract lets them go once a search has returned
+    SWB_CUDA(cudaStreamWaitEvent(st, db->ev_uploaded, 0));
+    if (n > 0) SWB_CUDA(cudaMemsetAsync(db->scores.p, 0, (size_t)n * sizeof(long long), st));
+    else SWB_CUDA(cudaStreamSynchronize(st));
   }
   else if (narrow)
   {
@@ -777,8 +822,79 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     nrequeue = n;
   }
 
-  if (n > 0)
+  if (hits && n > 0 && !use64)
   {
+    // The sink on the device: only the best `keep` (subject, score) pairs cross the bus.
+    SWB_TRY(db->hist.reserve(SWB_HIST_BINS + 1));
+    SWB_TRY(db->cand.reserve((size_t)n));
+    SWB_CUDA(cudaMemsetAsync(db->hist.p, 0, (SWB_HIST_BINS + 1) * sizeof(unsigned), st));
+    const unsigned hgrid = (unsigned)std::min<long long>((n + 256 * 16 - 1) / (256 * 16), (long long)db->sm_count * 8);
+    swb_hist_kernel<<<std::max(hgrid, 1u), 256, 0, st>>>(db->scores.p, n, tb.limit7, tb.limit16, hits->min_score,
+                                                         hits->upper, db->counters.p + 1, db->hist.p);
+    SWB_CUDA(cudaGetLastError());
+    swb_cut_kernel<<<1, 1024, 0, st>>>(db->hist.p, hits->keep, db->hist.p + SWB_HIST_BINS);
+    SWB_CUDA(cudaGetLastError());
+    launches += 2;
+    unsigned long long h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (hits->keep > 0)
+    {
+      swb_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+          db->scores.p, n, hits->min_score, hits->upper, db->hist.p + SWB_HIST_BINS, db->cand.p, db->counters.p + 6);
+      SWB_CUDA(cudaGetLastError());
+      launches++;
+    }
+    SWB_CUDA(cudaMemcpyAsync(h_cnt, db->counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+    SWB_CUDA(cudaStreamSynchronize(st));
+    c.ref_width7 = (long long)h_cnt[1];
+    c.ref_width16 = (long long)h_cnt[2];
+    c.ref_width63 = (long long)h_cnt[3];
+    hits->totalhits = (long long)h_cnt[4];
+    hits->obvious = (long long)h_cnt[5];
+    const long long ncand = (long long)h_cnt[6];
+    const long long take = std::min(ncand, hits->keep);
+    if (take > 0)
+    {
+      const unsigned long long *sorted = db->cand.p;
+      if (ncand > 1)
+      {
+        SWB_TRY(db->cand_sorted.reserve((size_t)ncand));
+        size_t tmp = 0;
+        SWB_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp, db->cand.p, db->cand_sorted.p, (int)ncand, 0, 64, st));
+        SWB_TRY(db->sort_tmp.reserve(tmp));
+        tmp = db->sort_tmp.cap;
+        SWB_CUDA(cub::DeviceRadixSort::SortKeysDescending(db->sort_tmp.p, tmp, db->cand.p, db->cand_sorted.p, (int)ncand, 0, 64, st));
+        launches += 4;
+        sorted = db->cand_sorted.p;
+      }
+      db->h_cand.resize((size_t)take);
+      SWB_CUDA(cudaMemcpyAsync(db->h_cand.data(), sorted, (size_t)take * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, st));
+      SWB_CUDA(cudaStreamSynchronize(st));
+      for (long long k = 0; k < take; k++)
+      {
+        hits->out_seqno[k] = hits->seqno_base + (long long)(db->h_cand[(size_t)k] & 0xffffffffull);
+        hits->out_score[k] = (long long)(db->h_cand[(size_t)k] >> 32);
+      }
+    }
+    hits->nhits = take;
+    if (qlen > 0)
+    {
+      float ms = 0;
+      SWB_CUDA(cudaEventElapsedTime(&ms, db->ev[0], db->ev[1]));
+      c.scan_ms = ms;
+      SWB_CUDA(cudaEventElapsedTime(&ms, db->ev[2], db->ev[3]));
+      c.requeue_ms = ms;
+    }
+  }
+  else if (n > 0)
+  {
+    std::vector<long long> dense;
+    if (hits && !scores)
+    {
+      // scores that may not fit the 32-bit half of a candidate key: dense read-back, host sink
+      dense.resize((size_t)n);
+      scores = dense.data();
+    }
     swb_widthcount_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
         db->scores.p, n, tb.limit7, tb.limit16, db->counters.p + 1);
     SWB_CUDA(cudaGetLastError());
@@ -805,6 +921,16 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       c.scan_ms = ms;
       SWB_CUDA(cudaEventElapsedTime(&ms, db->ev[2], db->ev[3]));
       c.requeue_ms = ms;
+    }
+    if (hits)
+    {
+      const int64_t *arr[1] = {(const int64_t *)scores};
+      const int64_t cnt[1] = {n}, base[1] = {hits->seqno_base};
+      int64_t tot = 0, obv = 0;
+      const int64_t k = swb_topk_merge(1, arr, cnt, base, hits->keep, hits->min_score, hits->upper,
+                                       (int64_t *)hits->out_seqno, (int64_t *)hits->out_score, &tot, &obv);
+      if (k < 0) return (int)k;
+      hits->nhits = k; hits->totalhits = tot; hits->obvious = obv;
     }
   }
   c.gpu_requeued = nrequeue;
@@ -1384,6 +1510,7 @@ int swb_db_close(swb_db *db)
   db->scores.release(); db->bestpos.release(); db->bestq.release(); db->requeue.release();
   db->list.release(); db->counters.release(); db->he.release(); db->bndH.release();
   db->bndF.release(); db->segs.release();
+  db->hist.release(); db->cand.release(); db->cand_sorted.release(); db->sort_tmp.release();
   for (int i = 0; i < 4; i++)
     if (db->ev[i]) cudaEventDestroy(db->ev[i]);
   for (int i = 0; i < 3; i++)
@@ -1424,6 +1551,64 @@ int swb_search_list(swb_db *db, const uint8_t *query, int64_t qlen, const swb_sc
   if (!db || (n > 0 && !seqnos)) return SWB_ERR_ARG;
   return search_impl(db, query, qlen, scoring, (const long long *)seqnos, n, (long long *)scores,
                      nullptr, nullptr, counters);
+}
+
+int swb_search_hits(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,
+                    int64_t seqno_base, int64_t keep, int64_t min_score, int64_t upper_score,
+                    int64_t *out_seqno, int64_t *out_score, int64_t *nhits, int64_t *totalhits,
+                    int64_t *obvious, swb_counters *counters)
+{
+  if (!db || keep < 0 || (keep > 0 && (!out_seqno || !out_score)) || !nhits) return SWB_ERR_ARG;
+  HitsReq H;
+  H.seqno_base = seqno_base; H.keep = keep; H.min_score = min_score; H.upper = upper_score;
+  H.out_seqno = (long long *)out_seqno; H.out_score = (long long *)out_score;
+  const int rc = search_impl(db, query, qlen, scoring, nullptr, db->nseq, nullptr, nullptr, nullptr,
+                             counters, &H);
+  if (rc != SWB_OK) return rc;
+  *nhits = H.nhits;
+  if (totalhits) *totalhits = H.totalhits;
+  if (obvious) *obvious = H.obvious;
+  return SWB_OK;
+}
+
+int64_t swb_hits_merge(int nlists, const int64_t *const *seqnos, const int64_t *const *scores,
+                       const int64_t *n, int64_t keep, int64_t *out_seqno, int64_t *out_score)
+{
+  if (nlists < 0 || keep < 0 || (nlists > 0 && (!seqnos || !scores || !n))) return SWB_ERR_ARG;
+  if (keep > 0 && (!out_seqno || !out_score)) return SWB_ERR_ARG;
+  // every list is already in the sink's order (score descending, then sequence number descending,
+  // hits.cc:188-191): a k-way merge by repeated selection of the best head; the lists are short
+  std::vector<int64_t> head((size_t)nlists, 0);
+  for (int s = 0; s < nlists; s++)
+    if (n[s] < 0 || (n[s] > 0 && (!seqnos[s] || !scores[s]))) return SWB_ERR_ARG;
+  int64_t out = 0;
+  while (out < keep)
+  {
+    int best = -1;
+    for (int s = 0; s < nlists; s++)
+    {
+      if (head[(size_t)s] >= n[s]) continue;
+      if (best < 0) { best = s; continue; }
+      const int64_t a = scores[s][head[(size_t)s]], b = scores[best][head[(size_t)best]];
+      if (a > b || (a == b && seqnos[s][head[(size_t)s]] > seqnos[best][head[(size_t)best]])) best = s;
+    }
+    if (best < 0) break;
+    out_seqno[out] = seqnos[best][head[(size_t)best]];
+    out_score[out] = scores[best][head[(size_t)best]];
+    head[(size_t)best]++;
+    out++;
+  }
+  return out;
+}
+
+int swb_set_cache_limit(int64_t bytes_per_device)
+{
+  if (bytes_per_device < 0) return SWB_ERR_ARG;
+  {
+    std::lock_guard<std::mutex> g(g_cache.mu);
+    g_cache.limit = bytes_per_device;
+  }
+  return SWB_OK;
 }
 
 int swb_search_end(swb_db *db, const uint8_t *query, int64_t qlen, const swb_scoring *scoring,

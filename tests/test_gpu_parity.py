@@ -318,3 +318,51 @@ def test_random_scoring_systems(oracle):
         residues, offsets = fixtures.pack(subs)
         with Database(residues, offsets) as db:
             _check(db, q, Scoring(m.reshape(-1), go, ge), oracle, residues, offsets, "fuzz %d" % it)
+
+
+@pytest.mark.parametrize("keep,min_score,upper", [(100, 1, 2 ** 62), (10, 40, 2 ** 62), (250, 0, 90),
+                                                   (5000, 1, 2 ** 62), (0, 30, 60), (64, 5000, 2 ** 62)])
+def test_device_sink_equals_hits_enter(oracle, keep, min_score, upper):
+    """swb_search_hits: the admission rule of hits_enter (hits.cc:163-222) applied on the device
+    returns the list the oracle's sink holds after seeing every score, ties included."""
+    q = synth.protein_query(200, seed=61)
+    residues, offsets = synth.protein_db(3000, query=q, seed=62, plant_every=40, max_len=500)
+    sc = Scoring(B62, 11, 1)
+    exp, _, _ = oracle.scan(residues, offsets, q, B62, 11, 1)
+    oseq, osc, otot, oobv = oracle.topk(np.arange(exp.size) + 1000, exp, keep, min_score=min_score, upper=upper)
+    with Database(residues, offsets) as db:
+        seq, s, tot, obv = db.search_hits(q, sc, keep, min_score, upper, seqno_base=1000)
+        c = db.last_counters
+    assert np.array_equal(seq, oseq) and np.array_equal(s, osc)
+    assert (tot, obv) == (otot, oobv)
+    assert c["ref_width7"] + c["ref_width16"] + c["ref_width63"] == exp.size
+
+
+def test_device_sink_with_requeued_scores_and_ties(oracle):
+    """Scores above the first histogram's range (re-queued self hits) and a database that is one
+    subject repeated (every score tied): the cut bin and the seqno tie rule must still hold."""
+    q = synth.protein_query(6000, seed=63)
+    rng = np.random.default_rng(64)
+    subs = [q[:L].copy() for L in (300, 800, 900, 5000, 6000)] + [synth.random_protein(rng, 77)] * 300
+    residues, offsets = fixtures.pack(subs)
+    sc = Scoring(B62, 11, 1)
+    exp, _, _ = oracle.scan(residues, offsets, q, B62, 11, 1)
+    for keep in (3, 5, 50, 1000):
+        oseq, osc, otot, _ = oracle.topk(np.arange(exp.size), exp, keep, min_score=1)
+        with Database(residues, offsets) as db:
+            seq, s, tot, _ = db.search_hits(q, sc, keep, 1)
+        assert np.array_equal(seq, oseq) and np.array_equal(s, osc) and tot == otot
+
+
+def test_list_with_repeated_subjects(oracle):
+    """A list may name a subject several times (search7.cc:894-895 only promises scores[k] <->
+    seqnos[k]); the list layout must size itself for the repeats."""
+    q = synth.protein_query(150, seed=71)
+    residues, offsets = synth.protein_db(40, query=q, seed=72, plant_every=5, min_len=25, max_len=3000)
+    lens = offsets[1:] - offsets[:-1]
+    longest = int(np.argmax(lens))
+    sel = np.array([longest] * 300 + [0, 1, longest, 2] * 20)
+    exp, _, _ = oracle.scan(residues, offsets, q, B62, 11, 1)
+    with Database(residues, offsets) as db:
+        got = db.search_list(q, Scoring(B62, 11, 1), sel)
+    assert np.array_equal(got, exp[sel])

@@ -99,3 +99,22 @@ def test_synthetic_inputs_are_deterministic_and_shaped():
     assert lens.min() >= 25 and lens.max() <= 5000 and 250 < lens.mean() < 450
     d, o = synth.dna_db(100)
     assert set(np.unique(d).tolist()) <= {1, 2, 4, 8} and (o[1:] - o[:-1]).min() >= 150
+
+
+def test_hits_merge_equals_the_dense_sink(oracle):
+    """swb_hits_merge over per-shard lists (each the shard's own top-K in the sink's order) gives
+    the list hits_enter would hold after seeing every subject (hits.cc:163-222)."""
+    rng = np.random.default_rng(21)
+    allsc = rng.integers(0, 40, size=5000)
+    cuts = [0, 1200, 1200, 3100, 5000]
+    lists = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        s, v, _, _ = swipe_b200.topk_merge([allsc[lo:hi]], [lo], keep=64, min_score=5, upper_score=38)
+        lists.append((s, v))
+    seq, sc = swipe_b200.hits_merge(lists, 64)
+    oseq, osc, _, _ = oracle.topk(np.arange(allsc.size), allsc, 64, min_score=5, upper=38)
+    assert np.array_equal(seq, oseq) and np.array_equal(sc, osc)
+    assert swipe_b200.hits_merge([], 10)[0].size == 0
+    assert swipe_b200.hits_merge(lists, 0)[0].size == 0
+    short, _ = swipe_b200.hits_merge([(np.array([7, 3]), np.array([9, 9]))], 10)
+    assert short.tolist() == [7, 3]
