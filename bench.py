@@ -1,25 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- GCUPS of the score-only Smith-Waterman database scan on N B200s.
 
-Workload (BASELINE.json configs[1]): a 375-aa background-frequency query, BLOSUM62, gap 11/1,
-against a synthetic 5,000,000-sequence protein database (log-normal lengths, ~1.75 G residues,
-0.1 % planted homologs) PER GPU.  With N GPUs every rank holds its own 5 M-sequence shard (weak
-scaling: a 5 M x N database sharded by sequence), there is no data-path collective, and rank 0
-merges the per-shard top-K lists with the reference's hits_enter rule.
+Workloads (BASELINE.json `configs`), selected with --config:
 
-  value : GCUPS = 1e-9 * residues * qlen / s (swipe.cc:1744-1775) with the shard resident in HBM;
-          K swb_search calls timed with CUDA events on the handle's stream, max over ranks.
-  e2e   : the same metric through the C ABI from HOST buffers: every step opens the shard
-          (pinned host -> device copy + device re-layout), searches, reads the scores back and
-          takes the local top-K.
-  --impl reference : the UNMODIFIED reference kernels (oracle/_ref, built from /root/reference)
-          on all host cores over a bounded sample of the same workload.
+  protein375 (default)  configs[1] at N=1: 375-aa query, BLOSUM62 11/1, 5,000,000-sequence synthetic
+                        protein database (log-normal lengths, ~1.76 G residues, 0.1 % planted homologs).
+                        At N>1 it is configs[4]: THE SAME database cut by residue count into N shards,
+                        one per GPU; every step each rank scans its shard and selects its hits on the
+                        device (swb_search_hits), the K (seqno, score) pairs per rank are gathered and
+                        rank 0 merges them with swb_hits_merge INSIDE the timed region ("scaling":
+                        "strong").  The merged list must equal the 1-GPU list (`topk_identical`).
+                        A secondary `weak` block times a full 5 M shard per GPU.
+  qlen100 / qlen1000 / qlen5000   configs[2]: the same database, other query lengths (N=1).
+  nt50m                 configs[3]: 1000-nt query, +1/-3, gaps 5/2, both strands (two scans, the second
+                        with the reverse-complemented query, query.cc:337-342) against 50 M reads (N=1).
+
+  value : GCUPS = 1e-9 * residues * qlen [* 2 strands] / s (swipe.cc:1744-1775), database resident in
+          HBM, K steps timed with CUDA events on the handle's stream, max over ranks.
+  e2e   : the same through the C ABI from pinned HOST buffers: every step opens the shard (host ->
+          device copy + device re-layout, overlapped with the scan), searches, and reads the hit
+          list back; with N>1 the gather and merge are inside as well.
+  roofline : the scan is bound by the issue rate of the packed 16x2 DPX instructions, which
+          swb_alu_peak measures in this run; HBM is reported as a secondary block.
+  --impl reference : the UNMODIFIED reference program (oracle/_ref/swipe, built from /root/reference)
+          on all host cores over a bounded sample of the same workload, its own "Speed:" line.
 """
 import argparse
 import json
 import os
+import re
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -28,10 +41,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-QLEN = 375
-NSEQ = 5_000_000
-GAP_OPEN, GAP_EXTEND = 11, 1
-TOPK = 100                                  # the reference keeps max(-v, -b) = 250 by default; any K works
+TOPK = 250                                  # the reference keeps max(-v, -b) = 250 hits by default (hits.cc:287)
+
+CONFIGS = {
+    "protein375": dict(kind="protein", qlen=375, nseq=5_000_000, gap_open=11, gap_extend=1,
+                       workload="375-aa query vs 5M-seq synthetic protein DB, BLOSUM62 11/1 (BASELINE configs[1]; "
+                                "sharded over the GPUs at N>1 = configs[4])"),
+    "qlen100": dict(kind="protein", qlen=100, nseq=5_000_000, gap_open=11, gap_extend=1,
+                    workload="100-aa query vs 5M-seq synthetic protein DB, BLOSUM62 11/1 (BASELINE configs[2])"),
+    "qlen1000": dict(kind="protein", qlen=1000, nseq=5_000_000, gap_open=11, gap_extend=1,
+                     workload="1000-aa query vs 5M-seq synthetic protein DB, BLOSUM62 11/1 (BASELINE configs[2])"),
+    "qlen5000": dict(kind="protein", qlen=5000, nseq=5_000_000, gap_open=11, gap_extend=1,
+                     workload="5000-aa query vs 5M-seq synthetic protein DB, BLOSUM62 11/1 (BASELINE configs[2])"),
+    "nt50m": dict(kind="nt", qlen=1000, nseq=50_000_000, gap_open=5, gap_extend=2,
+                  workload="1000-nt query, +1/-3, gaps 5/2, both strands vs 50M-read synthetic DNA DB "
+                           "(BASELINE configs[3])"),
+}
 
 
 def parse_args():
@@ -40,23 +65,56 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nseq", type=int, default=NSEQ, help="subjects per GPU shard")
-    ap.add_argument("--qlen", type=int, default=QLEN)
+    ap.add_argument("--config", default="protein375", choices=sorted(CONFIGS))
+    ap.add_argument("--nseq", type=int, default=0, help="override the database size (subjects)")
+    ap.add_argument("--qlen", type=int, default=0, help="override the query length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--no-product-path", action="store_true")
     ap.add_argument("--shape", default="", help="G,R,lane_mode test hook")
     return ap.parse_args()
 
 
-def make_workload(nseq, qlen, rank):
-    from swipe_b200 import synth
-    q = synth.protein_query(qlen)
-    residues, offsets = synth.protein_db(nseq, query=q, seed=20261018 + 1000 * rank)
-    return q, residues, offsets
+class Workload:
+    """The synthetic inputs of one config: queries (one per strand), database, scoring."""
+
+    def __init__(self, cfg, nseq, qlen):
+        from swipe_b200 import scoring, synth
+        self.kind = cfg["kind"]
+        self.gap_open, self.gap_extend = cfg["gap_open"], cfg["gap_extend"]
+        if self.kind == "protein":
+            q = synth.protein_query(qlen) if qlen == 375 else synth.protein_query(qlen, seed=20261017 + qlen)
+            self.queries = [q]
+            # planted homologs always derive from the 375-aa query so every config scans the same database
+            self.residues, self.offsets = synth.protein_db(nseq, query=synth.protein_query(375))
+            self.matrix = scoring.blosum62()
+            self.matrix_name = "BLOSUM62"
+        else:
+            q = synth.dna_query(qlen)
+            self.queries = [q, synth.revcomp_nt(q)]
+            self.residues, self.offsets = synth.dna_db_planted(nseq, q, ambiguity_every=10)
+            self.matrix = scoring.nucleotide_matrix(1, -3)
+            self.matrix_name = "+1/-3"
+        self.nseq = int(self.offsets.size - 1)
+        self.qlen = int(qlen)
+        self.total_res = int(self.offsets[-1])
+        self.cells = float(self.total_res) * self.qlen * len(self.queries)
+
+
+def shard_cuts(offsets, world):
+    """Sequence ranges [lo, hi) per rank holding equal shares of the residues (the cut swipe-b200 -a N
+    makes, swipe_main.cpp)."""
+    total = int(offsets[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(offsets, total * r // world, side="left")))
+    cuts.append(int(offsets.size - 1))
+    return [(max(cuts[r], cuts[r - 1] if r else 0), max(cuts[r + 1], cuts[r])) for r in range(world)]
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs (NVML, else nvidia-smi)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -73,7 +131,6 @@ class ClockSampler(threading.Thread):
             self._run_smi()
 
     def _run_nvml(self):
-        """NVML directly (nvidia-ml-py): a sample every 20 ms instead of one per nvidia-smi start-up."""
         import pynvml
         pynvml.nvmlInit()
         try:
@@ -120,49 +177,79 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def run_reference_cpu(q, residues, offsets, budget_s, threads):
-    """Times the reference's own search7/search16/fullsw cascade (oracle/_ref) on a bounded
-    prefix of the shard.  Returns (gcups, description)."""
+# ------------------------------------------------------------------------------------------------
+# CPU legs: the only places that touch oracle/ (test infrastructure used as the reported baseline)
+
+def harness_scan(w, budget_s, threads):
+    """The reference's own search7/search16/fullsw cascade (oracle/_ref, driven in memory by
+    oracle/ref_harness.cc) on a bounded prefix of the database, all strands.  Returns
+    (gcups, kind, description, [scores per strand])."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     kind = "reference" if oracle_lib.ref_available() else "port"
-    nseq = offsets.size - 1
-
     if kind == "reference":
         ref = oracle_lib.Ref()
-        ref.matrix_init("BLOSUM62")
+        if w.kind == "protein":
+            ref.matrix_init("BLOSUM62")
+        else:
+            ref.matrix_init("x", symtype=0, match=1, mismatch=-3)
 
-        def scan(n):
-            return ref.scan(residues[: offsets[n]], offsets[: n + 1], q, GAP_OPEN, GAP_EXTEND,
-                            threads=threads, chunk=1024, ssse3=1)
+        def scan(n, q):
+            return ref.scan(w.residues[: w.offsets[n]], w.offsets[: n + 1], q, w.gap_open, w.gap_extend,
+                            threads=threads, chunk=1024, ssse3=1)[0]
     else:
-        from swipe_b200 import scoring
         orc = oracle_lib.Oracle()
-        m = scoring.blosum62()
 
-        def scan(n):
-            return orc.scan(residues[: offsets[n]], offsets[: n + 1], q, m, GAP_OPEN, GAP_EXTEND,
-                            threads=threads)
+        def scan(n, q):
+            return orc.scan(w.residues[: w.offsets[n]], w.offsets[: n + 1], q, w.matrix, w.gap_open,
+                            w.gap_extend, threads=threads)[0]
 
-    n0 = min(nseq, 20000)
-    scan(n0)                                   # cold: page faults, thread start-up
+    n0 = min(w.nseq, 20000)
+    scan(n0, w.queries[0])                     # cold: page faults, thread start-up
     t0 = time.perf_counter()
-    scan(n0)
-    t1 = time.perf_counter()
-    rate = float(offsets[n0]) * q.size / max(t1 - t0, 1e-6)          # cells / s, cold
-    n = int(min(nseq, max(n0, budget_s * rate / (q.size * (offsets[n0] / n0)))))
+    scan(n0, w.queries[0])
+    rate = float(w.offsets[n0]) * w.qlen / max(time.perf_counter() - t0, 1e-6)       # cells / s
+    per_seq = w.qlen * (w.offsets[n0] / n0) * len(w.queries)
+    n = int(min(w.nseq, max(n0, budget_s * rate / per_seq)))
     t0 = time.perf_counter()
-    out = scan(n)
-    t1 = time.perf_counter()
-    cells = float(offsets[n]) * q.size
-    run_reference_cpu.last_scores = np.asarray(out[0][:n])      # kept for the bench's full-size parity check
-    return cells / (t1 - t0) * 1e-9, kind, "first %d subjects (%d residues) of the shard, %.1f s" % (
-        n, int(offsets[n]), t1 - t0)
+    outs = [np.asarray(scan(n, q)[:n]) for q in w.queries]
+    dt = time.perf_counter() - t0
+    cells = float(w.offsets[n]) * w.qlen * len(w.queries)
+    return cells / dt * 1e-9, kind, "first %d subjects (%d residues) of the database, %d strand(s), %.1f s" % (
+        n, int(w.offsets[n]), len(w.queries), dt), outs
+
+
+def write_blast_sample(w, n, basename):
+    """The first n subjects as a BLAST v4 database the unmodified reference program reads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import blastdb
+    if w.kind == "protein":
+        blastdb.write_protein_fast(basename, w.residues[: w.offsets[n]], w.offsets[: n + 1])
+    else:
+        blastdb.write_nucleotide_fast(basename, w.residues[: w.offsets[n]], w.offsets[: n + 1])
+    blastdb.write_fasta(basename + ".query.fa", w.queries[0], protein=w.kind == "protein")
+
+
+def reference_cli(w, basename, threads):
+    """One run of oracle/_ref/swipe -a threads -v 10 -b 0 (alignment phase idle):
+    (its own "Speed:" GCUPS, its "Elapsed:" seconds, external wall seconds)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "swipe")
+    cmd = [exe, "-d", basename, "-i", basename + ".query.fa", "-a", str(threads), "-v", "10", "-b", "0"]
+    if w.kind == "nt":
+        cmd += ["-p", "0", "-r", "1", "-q", "-3"]
+    t0 = time.perf_counter()
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1800).stdout
+    wall = time.perf_counter() - t0
+    m = re.search(r"Speed:\s+([0-9.]+) GCUPS", out)
+    e = re.search(r"Elapsed:\s+([0-9.]+)s", out)
+    if not m:
+        raise RuntimeError("reference program printed no Speed line:\n" + out[-2000:])
+    return float(m.group(1)), float(e.group(1)) if e else 0.0, wall
 
 
 def bind_to_gpu_numa_node(index):
     """Multi-rank runs: keep this rank's host threads and its pinned buffers on the NUMA node the GPU
-    hangs off, so that eight simultaneous uploads do not cross sockets.  Best effort."""
+    hangs off, so that simultaneous uploads do not cross sockets.  Best effort."""
     try:
         import torch
         p = torch.cuda.get_device_properties(index)
@@ -181,53 +268,98 @@ def bind_to_gpu_numa_node(index):
         pass
 
 
+def base_config(args, cfg, w_nseq, qlen, world):
+    return {"workload": cfg["workload"], "name": args.config, "qlen": qlen, "nseq": w_nseq,
+            "strands": 2 if cfg["kind"] == "nt" else 1,
+            "gap_open": cfg["gap_open"], "gap_extend": cfg["gap_extend"],
+            "matrix": "BLOSUM62" if cfg["kind"] == "protein" else "+1/-3",
+            "sharding": "one database cut by residue count into %d shard(s), no data-path collective; "
+                        "K (seqno, score) pairs per rank gathered and merged on the host" % world,
+            "keep": TOPK,
+            "l2": "inputs (%.1f GB database) larger than L2" % (w_nseq * (350 if cfg["kind"] == "protein" else 200) / 1e9),
+            "lanes": "two int16 lanes per 32-bit register: DPX s16x2 max / add-max, adds as fp16x2 on integer "
+                     "bit patterns (exact to 2047), re-queue to plain int16 lanes and then 32/64-bit cells"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, cfg, nseq, qlen):
+    """The reference arm: the unmodified program's own number on this box's host cores."""
+    cores = os.cpu_count() or 1
+    sample = min(nseq, 2_000_000 if cfg["kind"] == "protein" else 8_000_000)
+    if qlen >= 1000 and cfg["kind"] == "protein":
+        sample = min(sample, 1_000_000)
+    w = Workload(cfg, sample, qlen)
+    config = base_config(args, cfg, nseq, qlen, 1)
+    exe = os.path.join(ROOT, "oracle", "_ref", "swipe")
+    line = {"metric": "GCUPS", "unit": "GCUPS", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "int8",
+            "data": "synthetic", "config": config}
+    if os.path.exists(exe):
+        tmp = tempfile.mkdtemp(prefix="swb_ref_")
+        try:
+            base = os.path.join(tmp, "db")
+            write_blast_sample(w, w.nseq, base)
+            speeds, elapsed, walls = [], [], []
+            for it in range(args.warmup + args.steps):
+                s, e, wl = reference_cli(w, base, cores)
+                if it >= args.warmup:
+                    speeds.append(s); elapsed.append(e); walls.append(wl)
+            # one thread, on a tenth of the sample (per-core figure, BASELINE.md section 3)
+            n1 = max(1000, w.nseq // 10)
+            base1 = os.path.join(tmp, "db1")
+            w1 = w
+            if n1 < w.nseq:
+                write_blast_sample(w, n1, base1)
+            else:
+                base1 = base
+            s1, _, _ = reference_cli(w1, base1, 1)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        v = float(np.median(speeds))
+        cells = w.cells
+        # "Speed" is cells / the program's own Elapsed (10 ms ticks): the step time is its search phase
+        ms = float(np.median(elapsed)) * 1e3
+        desc = ("oracle/_ref/swipe -a %d -v 10 -b 0 on the first %d subjects (%d residues) written as a BLAST v4 "
+                "database; median of %d runs of its own Speed line" % (cores, w.nseq, w.total_res, len(speeds)))
+        line.update({"value": v, "ms_per_step": ms,
+                     "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": cores, "kind": "reference", "sample": desc,
+                                      "best": float(np.max(speeds)), "median": v, "runs": [round(x, 2) for x in speeds],
+                                      "one_thread_gcups": s1, "wall_s_median": float(np.median(walls)),
+                                      "elapsed_s_median": float(np.median(elapsed)), "cells_per_step": cells}})
+    else:
+        vals = []
+        desc = kind = ""
+        t0 = time.perf_counter()
+        for it in range(args.warmup + args.steps):
+            g, kind, desc, _ = harness_scan(w, 6.0, cores)
+            if it >= args.warmup:
+                vals.append(g)
+        v = float(np.median(vals))
+        line.update({"value": v, "ms_per_step": (time.perf_counter() - t0) * 1e3 / max(1, args.warmup + args.steps),
+                     "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": desc}})
+    line["e2e"] = {"value": line["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    cfg = dict(CONFIGS[args.config])
+    nseq = args.nseq or cfg["nseq"]
+    qlen = args.qlen or cfg["qlen"]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    config = {"workload": "375-aa query vs 5M-seq synthetic protein DB per GPU, BLOSUM62 11/1 "
-                          "(BASELINE configs[1])",
-              "qlen": args.qlen, "nseq_per_gpu": args.nseq, "gap_open": GAP_OPEN,
-              "gap_extend": GAP_EXTEND, "matrix": "BLOSUM62", "sharding": "by sequence, no collective",
-              "l2": "inputs (1.8 GB/shard) larger than L2",
-              "lanes": "two int16 lanes per 32-bit register: DPX s16x2 max / add-max, adds as fp16x2 on integer "
-                       "bit patterns (exact to 2047), re-queue to plain int16 lanes and then 32/64-bit cells"}
 
-    # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        q, residues, offsets = make_workload(min(args.nseq, 1_000_000), args.qlen, 0)
-        vals = []
-        desc = kind = ""
-        budget = 8.0
-        for it in range(args.warmup + args.steps):
-            g, kind, desc = run_reference_cpu(q, residues, offsets, budget, cores)
-            if it >= args.warmup:
-                vals.append(g)
-            if it == 0 and args.warmup + args.steps > 12:
-                budget = 4.0
-        v = float(np.mean(vals)) if vals else 0.0
-        # one "step" of the metric's workload (a 5 M-sequence shard) at the measured rate
-        ms = (1.75e9 * args.qlen / (v * 1e9)) * 1e3 if v > 0 else 0.0
-        line = {"metric": "GCUPS", "value": v, "unit": "GCUPS", "impl": "reference",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "int8",
-                "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": cores, "kind": kind,
-                                 "sample": desc},
-                "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
+        return run_reference(args, cfg, nseq, qlen) if rank == 0 else 0
 
-    # ------------------------------------------------------------------ B200 arm
     import torch
     import torch.distributed as dist
-    from swipe_b200 import Database, Scoring, HostBuffer, scoring, topk_merge
+    from swipe_b200 import (Database, Scoring, HostBuffer, topk_merge, hits_merge, set_cache_limit, alu_peak)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the scan has no CPU path")
@@ -236,189 +368,360 @@ def main():
         bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    q, residues, offsets = make_workload(args.nseq, args.qlen, rank)
-    nseq = offsets.size - 1
-    total_res = int(offsets[-1])
-    cells = float(total_res) * args.qlen
-    sc = Scoring(scoring.blosum62(), GAP_OPEN, GAP_EXTEND)
+    if cfg["kind"] == "nt":
+        import psutil
+        avail = psutil.virtual_memory().available
+        if avail < nseq * 200 * 3.2:                    # codes + pinned copy + generator scratch
+            nseq = int(avail // (200 * 3.2))
+        set_cache_limit(64 << 30)                       # the e2e loop re-opens a 10 GB shard every step
+    w = Workload(cfg, nseq, qlen)
+    config = base_config(args, cfg, w.nseq, qlen, world)
+    sc = Scoring(w.matrix, w.gap_open, w.gap_extend)
+    nq = len(w.queries)
 
-    # pinned host copies: what a caller that mmaps the .psq would hand over
-    pin_res = HostBuffer(total_res)
-    pin_res.u8[:] = residues
-    pin_off = HostBuffer(8 * (nseq + 1))
-    pin_off.view(np.int64)[:] = offsets
-    pin_scores = HostBuffer(8 * nseq)
-    scores = pin_scores.view(np.int64)
+    # this rank's shard of the one database
+    lo, hi = shard_cuts(w.offsets, world)[rank]
+    sh_off = (w.offsets[lo: hi + 1] - w.offsets[lo]).astype(np.int64)
+    sh_nseq = hi - lo
+    sh_res = int(sh_off[-1])
+    pin_res = HostBuffer(max(sh_res, 1))
+    pin_res.u8[:sh_res] = w.residues[w.offsets[lo]: w.offsets[hi]]
+    pin_off = HostBuffer(8 * (sh_nseq + 1))
+    pin_off.view(np.int64)[:] = sh_off
+    if cfg["kind"] == "nt":
+        w.residues = None                               # the pinned copy is the database from here on
 
     stream = torch.cuda.Stream()
     shape = [int(x) for x in args.shape.split(",")] if args.shape else None
+    gather_buf = torch.empty((TOPK * nq, 2), dtype=torch.int64).pin_memory()
+    gather_dev = torch.empty((TOPK * nq, 2), dtype=torch.int64, device="cuda")
+    gathered_dev = [torch.empty_like(gather_dev) for _ in range(world)] if world > 1 else None
+    gathered_host = torch.empty((world, TOPK * nq, 2), dtype=torch.int64).pin_memory() if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-database timing ------------------------------------------------------------
-    db = Database(pin_res.u8, pin_off.view(np.int64), device=local_rank, stream=stream.cuda_stream)
+    split = {"search": 0.0, "gather": 0.0, "merge": 0.0}
+
+    def step(db, record=None):
+        """One pass of the hot path over this rank's shard: scan(s) + device sink, then the exchange of
+        the per-rank hit lists and the merge on rank 0.  Returns rank 0's merged (seqnos, scores)."""
+        t0 = time.perf_counter()
+        lists = []
+        for s, q in enumerate(w.queries):
+            seq, scv, tot, obv = db.search_hits(q, sc, TOPK, 1, 2 ** 62, seqno_base=lo)
+            lists.append((seq * nq + s, scv))            # strand in the low bit keeps (seqno, strand) unique
+            if record is not None:
+                c = db.last_counters
+                record["launches"] += c["kernel_launches"]
+                record["scan_ms"].append(c["scan_ms"])
+                record["requeue_ms"].append(c["requeue_ms"])
+                record["counters"] = c
+        t1 = time.perf_counter()
+        merged = None
+        if world > 1:
+            with torch.cuda.stream(stream):
+                gather_buf.fill_(-1)
+                at = 0
+                for seq, scv in lists:
+                    gather_buf[at: at + seq.size, 0] = torch.from_numpy(seq)
+                    gather_buf[at: at + seq.size, 1] = torch.from_numpy(scv)
+                    at += TOPK
+                gather_dev.copy_(gather_buf, non_blocking=True)
+                dist.all_gather(gathered_dev, gather_dev)
+                if rank == 0:
+                    for r in range(world):
+                        gathered_host[r].copy_(gathered_dev[r], non_blocking=True)
+            stream.synchronize()
+            t2 = time.perf_counter()
+            if rank == 0:
+                g = gathered_host.numpy()
+                parts = []
+                for r in range(world):
+                    for s in range(nq):
+                        blk = g[r, s * TOPK: (s + 1) * TOPK]
+                        k = int((blk[:, 0] >= 0).sum())
+                        parts.append((blk[:k, 0], blk[:k, 1]))
+                merged = hits_merge(parts, TOPK)
+        else:
+            t2 = t1
+            merged = hits_merge(lists, TOPK) if nq > 1 else lists[0]
+        t3 = time.perf_counter()
+        split["search"] += t1 - t0
+        split["gather"] += t2 - t1
+        split["merge"] += t3 - t2
+        return merged
+
+    # ---- the 1-GPU answer the sharded run must reproduce (rank 0, outside the timed region) ----------
+    single = None
+    dense_checksum = None
+    if rank == 0 and world > 1:
+        with Database(w.residues, w.offsets, device=local_rank) as full:
+            ls = []
+            for s, q in enumerate(w.queries):
+                seq, scv, _, _ = full.search_hits(q, sc, TOPK, 1, 2 ** 62)
+                ls.append((seq * nq + s, scv))
+            single = hits_merge(ls, TOPK)
+
+    # ---- resident-database timing ------------------------------------------------------------------
+    db = Database(pin_res.u8[:sh_res], pin_off.view(np.int64), device=local_rank, stream=stream.cuda_stream)
     if shape:
         db.set_shape(*shape)
     for _ in range(args.warmup):
-        db.search(q, sc, out=scores)
+        step(db)
+    rec = {"launches": 0, "scan_ms": [], "requeue_ms": [], "counters": None}
+    for k in split:
+        split[k] = 0.0
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    scan_ms = []
-    requeue_ms = []
     e0.record(stream)
+    merged = None
     for _ in range(args.steps):
-        db.search(q, sc, out=scores)
-        c = db.last_counters
-        launches += c["kernel_launches"]
-        scan_ms.append(c["scan_ms"])
-        requeue_ms.append(c["requeue_ms"])
+        merged = step(db, rec)
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
     my_ms = e0.elapsed_time(e1)
-    counters = db.last_counters
-    checksum = int(scores.sum())
-    top_seq, top_sc, _, _ = topk_merge([scores], [rank * nseq], TOPK, min_score=1)
+    res_split = {k: v * 1e3 / args.steps for k, v in split.items()}
+
+    # ---- parity of the sink at full size: dense scores of the last query + host sink (rank-local) ----
+    pin_scores = HostBuffer(8 * max(sh_nseq, 1))
+    dense = pin_scores.view(np.int64)[:sh_nseq]
+    local_lists = []
+    for s, q in enumerate(w.queries):
+        db.search(q, sc, out=dense)
+        seq, scv, _, _ = topk_merge([dense], [lo], TOPK, min_score=1)
+        local_lists.append((seq * nq + s, scv))
+        hseq, hsc, _, _ = db.search_hits(q, sc, TOPK, 1, 2 ** 62, seqno_base=lo)
+        if not (np.array_equal(hseq, seq) and np.array_equal(hsc, scv)):
+            raise SystemExit("bench.py: device sink differs from the host sink on rank %d" % rank)
+        if s == 0:
+            dense_checksum = int(dense.sum())
+    topk_identical = None
+    if rank == 0:
+        if world > 1:
+            topk_identical = bool(np.array_equal(merged[0], single[0]) and np.array_equal(merged[1], single[1]))
+        else:
+            ref_list = hits_merge(local_lists, TOPK)
+            topk_identical = bool(np.array_equal(merged[0], ref_list[0]) and np.array_equal(merged[1], ref_list[1]))
+    dense_first_strand = None
+    if world == 1 and not args.no_cpu_baseline:
+        db.search(w.queries[0], sc, out=dense)
+        dense_first_strand = dense.copy() if nq > 1 else dense
     db.close()
 
-    # ---- end to end from host buffers ---------------------------------------------------------
+    # ---- end to end from host buffers ------------------------------------------------------------------
     e2e_ms = None
-    h2d = total_res + 8 * (nseq + 1) + args.qlen + 8 * 1024 + 33 * 32 * 2 + 2 * 1024
-    d2h = 8 * nseq + 64
+    e2e_split = None
+    h2d = sh_res + 8 * (sh_nseq + 1) + nq * (qlen + 8 * 1024 + 2256 + 2 * 1024)
+    d2h = nq * (16 * TOPK + 64)
     if not args.no_e2e:
-        split = np.zeros(4)
+        host = {"open_enqueue": 0.0, "search_gather_merge": 0.0, "close": 0.0}
 
         def e2e_step():
             t0 = time.perf_counter()
-            d = Database(pin_res.u8, pin_off.view(np.int64), device=local_rank,
+            d = Database(pin_res.u8[:sh_res], pin_off.view(np.int64), device=local_rank,
                          stream=stream.cuda_stream, wait=False)   # upload / re-layout / scan overlap
             if shape:
                 d.set_shape(*shape)
             t1 = time.perf_counter()
-            d.search(q, sc, out=scores)
+            step(d)
             t2 = time.perf_counter()
-            k = d.last_counters["kernel_launches"]
             d.close()
             t3 = time.perf_counter()
-            topk_merge([scores], [rank * nseq], TOPK, min_score=1)
-            t4 = time.perf_counter()
-            split[:] += (t1 - t0, t2 - t1, t3 - t2, t4 - t3)
-            return k
+            host["open_enqueue"] += t1 - t0
+            host["search_gather_merge"] += t2 - t1
+            host["close"] += t3 - t2
         for _ in range(max(1, min(args.warmup, 2))):
             e2e_step()
+        for k in host:
+            host[k] = 0.0
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        split[:] = 0
         f0.record(stream)
         for _ in range(args.steps):
             e2e_step()
         f1.record(stream)
         barrier()
         e2e_ms = f0.elapsed_time(f1)
+        e2e_split = {k: round(v * 1e3 / args.steps, 3) for k, v in host.items()}
 
-    # ---- reduce over ranks ----------------------------------------------------------------------
+    # ---- weak scaling, secondary: every GPU scans a full copy of the database -------------------------
+    weak_ms = None
+    weak_steps = max(1, min(args.steps, 5))
+    if world > 1 and not args.no_weak and w.residues is not None:
+        with Database(w.residues, w.offsets, device=local_rank, stream=stream.cuda_stream) as full:
+            full.search_hits(w.queries[0], sc, TOPK, 1, 2 ** 62)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(weak_steps):
+                for q in w.queries:
+                    full.search_hits(q, sc, TOPK, 1, 2 ** 62)
+            g1.record(stream)
+            barrier()
+            weak_ms = g0.elapsed_time(g1)
+
+    # ---- the product's own multi-GPU path, secondary: ONE process, one host thread + handle per GPU ----
+    # (what swipe-b200 -a N does, swipe_main.cpp); rank 0 drives all N devices while the other ranks wait.
+    product = None
     if world > 1:
-        t = torch.tensor([my_ms, e2e_ms or 0.0, cells, float(launches)], device="cuda",
-                         dtype=torch.float64)
+        barrier()
+        if rank == 0 and not args.no_product_path and torch.cuda.device_count() >= world:
+            cuts = shard_cuts(w.offsets, world)
+            dbs = []
+            for r, (a, b) in enumerate(cuts):
+                dbs.append((a, Database(w.residues[w.offsets[a]: w.offsets[b]],
+                                        (w.offsets[a: b + 1] - w.offsets[a]).astype(np.int64), device=r)))
+            out = [None] * world
+
+            def worker(r):
+                a, d = dbs[r]
+                ls = []
+                for s, q in enumerate(w.queries):
+                    seq, scv, _, _ = d.search_hits(q, sc, TOPK, 1, 2 ** 62, seqno_base=a)
+                    ls.append((seq * nq + s, scv))
+                out[r] = ls
+
+            def product_step():
+                th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                return hits_merge([l for ls in out for l in ls], TOPK)
+            for _ in range(2):
+                product_step()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                pm = product_step()
+            dt = time.perf_counter() - t0
+            for _, d in dbs:
+                d.close()
+            torch.cuda.set_device(local_rank)            # the handles switched this thread's device
+            product = {"value": w.cells * args.steps / dt * 1e-9, "unit": "GCUPS", "ms_per_step": dt * 1e3 / args.steps,
+                       "timing": "host wall clock around N threads (each search ends in a stream synchronize)",
+                       "topk_identical": bool(np.array_equal(pm[0], single[0]) and np.array_equal(pm[1], single[1])),
+                       "what": "one process, one host thread + swb_db handle per GPU, swb_search_hits + swb_hits_merge"}
+        barrier()
+
+    # ---- reduce over ranks --------------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([my_ms, e2e_ms or 0.0, weak_ms or 0.0, float(rec["launches"]), float(np.mean(rec["scan_ms"])),
+                          res_split["search"], float(sh_res)], device="cuda", dtype=torch.float64)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_all, e2e_all = float(tmax[0]), float(tmax[1])
-        cells_all, launches_all = float(tsum[2]), int(tsum[3])
-        # host-side top-K merge of the shards (hits_enter rule): gather K (seqno, score) per rank
-        mine = torch.full((TOPK, 2), -1, dtype=torch.int64, device="cuda")
-        mine[: top_seq.size, 0] = torch.from_numpy(top_seq).cuda()
-        mine[: top_seq.size, 1] = torch.from_numpy(top_sc).cuda()
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        if rank == 0:
-            allhits = torch.cat(gathered).cpu().numpy()
-            allhits = allhits[allhits[:, 0] >= 0]
-            order = np.lexsort((-allhits[:, 0], -allhits[:, 1]))[:TOPK]
-            top_seq, top_sc = allhits[order, 0], allhits[order, 1]
+        ms_all, e2e_all, weak_all = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        launches_all = int(tsum[3])
+        scan_max, search_max = float(tmax[4]), float(tmax[5])
+        h2d_all, d2h_all = int(tsum[6]) + world * (h2d - sh_res), d2h * world
     else:
-        ms_all, e2e_all, cells_all, launches_all = my_ms, e2e_ms, cells, launches
+        ms_all, e2e_all, weak_all, launches_all = my_ms, e2e_ms, None, rec["launches"]
+        scan_max, search_max = float(np.mean(rec["scan_ms"])), res_split["search"]
+        h2d_all, d2h_all = h2d, d2h
 
     if rank == 0:
-        value = cells_all * args.steps / (ms_all * 1e-3) * 1e-9
-        scan_avg = float(np.mean(scan_ms))
+        value = w.cells * args.steps / (ms_all * 1e-3) * 1e-9
+        scan_avg = float(np.mean(rec["scan_ms"]))            # per scan launch (one strand), this rank
+        my_cells_per_scan = float(sh_res) * qlen
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        # the binding roofline: issue rate of the DPX instructions, measured now on this device
+        dpx_rate, ub_mhz = alu_peak(local_rank)
+        sm_mhz = clocks["sm_mhz"] or ub_mhz or 1965.0
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        dpx_per_cell_pair = 3.5                              # 1 VIMNMX3 + 2 VIADDMNMX + 1/2 VIMNMX3 (running maximum)
+        peak_cells_clk_sm = dpx_rate * 64.0 / dpx_per_cell_pair
+        peak_gcups = peak_cells_clk_sm * sms * sm_mhz * 1e6 * 1e-9
+        kernel_gcups = my_cells_per_scan / (scan_avg * 1e-3) * 1e-9
+        cells_clk_sm = my_cells_per_scan / (scan_avg * 1e-3) / (sms * sm_mhz * 1e6)
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes = total_res + 8 * nseq                 # 1 B per residue + 8 B per subject
-        achieved = alg_bytes / (scan_avg * 1e-3) * 1e-9
-        # DRAM traffic of the scan kernel from the committed ncu --set full capture, scaled from the
-        # captured shard to this one by algorithmic bytes (the kernel streams every block once)
+        alg_bytes = sh_res + 8 * sh_nseq                     # SURVEY 8(d): 1 B per residue + 8 B per subject
+        hbm_achieved = alg_bytes / (scan_avg * 1e-3) * 1e-9
         traffic = None
+        traffic_src = None
         try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-            cap_alg = cap["residues"] + 8 * cap["subjects"]
-            traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * (alg_bytes / cap_alg)
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+            for c in cap["captures"]:
+                if c["config"] == args.config and c["subjects"] == sh_nseq and c["residues"] == sh_res:
+                    traffic = c["dram_bytes_read"] + c["dram_bytes_write"]
+                    traffic_src = c["source"]
         except Exception:
             pass
-        sm_mhz = clocks["sm_mhz"] or 1965.0
-        cells_per_clk_sm = cells / (scan_avg * 1e-3) / (148 * sm_mhz * 1e6)
         line = {
             "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "int16",
             "data": "synthetic", "config": config, "clocks": clocks,
             "gpu_launches": launches_all,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic,
-                         "traffic_source": "profiles/r1_ncu_traffic.json (ncu capture at 1.5M subjects, scaled by algorithmic bytes)",
-                         "algorithmic_bytes": alg_bytes,
-                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+            "roofline": {"bound": "int-alu-issue", "achieved": kernel_gcups, "peak": peak_gcups, "unit": "GCUPS",
+                         "frac": kernel_gcups / peak_gcups,
                          "kernel": "swb_scan_kernel", "kernel_ms": scan_avg,
-                         "note": "integer-issue bound, not HBM bound (SURVEY 8d): see alu"},
-            "alu": {"kernel_gcups": cells / (scan_avg * 1e-3) * 1e-9,
-                    "cells_per_clk_per_sm": cells_per_clk_sm,
-                    "lane_ops_per_cell": 9,
-                    "peak_cells_per_clk_per_sm_ubench_int16": 25.6,
-                    "peak_cells_per_clk_per_sm_ubench_hybrid": 29.9,
-                    "frac_of_ubench_hybrid": cells_per_clk_sm / 29.9,
-                    # 3.5 DPX ops per cell pair at one warp instruction per 2 clk on the 16-lane ALU
-                    # pipe = 7 clk per 64 cells per SM sub-partition
-                    "alu_pipe_bound_cells_per_clk_per_sm": 4 * 64 / 7.0,
-                    "frac_of_alu_pipe_bound": cells_per_clk_sm / (4 * 64 / 7.0),
-                    "nominal_8bit_tcups": 8.27,
-                    "frac_of_nominal_8bit": cells / (scan_avg * 1e-3) * 1e-12 / 8.27},
-            "counters": {k: counters[k] for k in ("ref_width7", "ref_width16", "ref_width63",
-                                                   "gpu_narrow", "gpu_requeued", "kernel_launches")},
-            "requeue_ms": float(np.mean(requeue_ms)),
-            "checksum": checksum, "top_hit": [int(top_seq[0]), int(top_sc[0])] if len(top_seq) else None,
+                         "cells_per_launch": my_cells_per_scan, "cells_per_clk_per_sm": cells_clk_sm,
+                         "peak_cells_per_clk_per_sm": peak_cells_clk_sm,
+                         "dpx_warp_instr_per_clk_per_sm_measured": dpx_rate, "dpx_per_cell_pair": dpx_per_cell_pair,
+                         "lane_ops_per_cell": 9, "sm_mhz": sm_mhz, "ubench_sm_mhz": ub_mhz, "sms": sms,
+                         "peak_source": "swb_alu_peak in this run (issue rate of VIADDMNMX/VIMNMX3.S16x2) x 64 cells / 3.5 "
+                                        "DPX per cell pair x SMs x median SM clock of the timed region",
+                         "nominal_8bit_x4_gcups": 64 * 4 / 9.0 * sms * sm_mhz * 1e-3,
+                         "frac_of_nominal_8bit_x4": kernel_gcups / (64 * 4 / 9.0 * sms * sm_mhz * 1e-3),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": hbm_achieved / hbm_peak, "algorithmic_bytes": alg_bytes,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                                 "note": "not the binding bound (SURVEY 8d): 1 byte per residue per scan"}},
+            "split_ms": {"scan_kernel_max_over_ranks": scan_max * nq, "search_call_max_over_ranks": search_max,
+                         "sink_and_d2h": max(0.0, search_max - scan_max * nq), "gather": res_split["gather"],
+                         "merge": res_split["merge"], "step": ms_all / args.steps},
+            "counters": {k: rec["counters"][k] for k in ("ref_width7", "ref_width16", "ref_width63", "gpu_narrow",
+                                                         "gpu_requeued", "gpu_middle", "kernel_launches")},
+            "requeue_ms": float(np.mean(rec["requeue_ms"])),
+            "topk_identical": topk_identical, "checksum": dense_checksum,
+            "top_hit": [int(merged[0][0]) // nq, int(merged[1][0])] if len(merged[0]) else None,
         }
+        sp = line["split_ms"]
+        parts = {"scan": sp["scan_kernel_max_over_ranks"], "sink_and_d2h": sp["sink_and_d2h"],
+                 "gather": sp["gather"], "merge": sp["merge"]}
+        line["split_ms"]["limiter"] = max(parts, key=parts.get)
         if e2e_all:
-            line["e2e"] = {"value": cells_all * args.steps / (e2e_all * 1e-3) * 1e-9, "unit": "GCUPS",
-                           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                           "ms_per_step": e2e_all / args.steps,
-                           "host_ms": dict(zip(["open_enqueue", "search", "close", "topk"],
-                                               [round(float(x) * 1e3 / args.steps, 2) for x in split]))}
+            line["e2e"] = {"value": w.cells * args.steps / (e2e_all * 1e-3) * 1e-9, "unit": "GCUPS",
+                           "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+                           "ms_per_step": e2e_all / args.steps, "host_ms": e2e_split}
+        if weak_all:
+            line["weak"] = {"value": w.cells * world * weak_steps / (weak_all * 1e-3) * 1e-9, "unit": "GCUPS",
+                            "ms_per_step": weak_all / weak_steps, "steps": weak_steps,
+                            "what": "every GPU scans its own full copy of the database (per-GPU work fixed)"}
+        if product:
+            line["product_path"] = product
         if world == 1 and not args.no_cpu_baseline:
-            g, kind, desc = run_reference_cpu(q, residues, offsets, 12.0, cores)
-            line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": kind,
-                                    "sample": desc}
-            # the CPU leg scored the same subjects: a bit-exact parity check at the bench's full size
-            ref_scores = getattr(run_reference_cpu, "last_scores", None)
-            if ref_scores is not None:
-                k = int(ref_scores.size)
-                line["cpu_baseline"]["scores_compared"] = k
-                line["cpu_baseline"]["scores_equal"] = bool(np.array_equal(ref_scores, scores[:k]))
+            budget = 12.0
+            g, kind, desc, outs = harness_scan(w if w.residues is not None else _host_view(w, pin_res, sh_res),
+                                               budget, cores)
+            line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": desc}
+            # the CPU leg scored the same subjects: a bit-exact parity check at the bench's own size
+            k = int(outs[0].size)
+            line["cpu_baseline"]["scores_compared"] = k * 1
+            line["cpu_baseline"]["scores_equal"] = bool(np.array_equal(outs[0], dense_first_strand[:k]))
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _host_view(w, pin_res, sh_res):
+    """nt50m drops the pageable copy of the database; the CPU leg reads the pinned one."""
+    w.residues = pin_res.u8[:sh_res]
+    return w
 
 
 if __name__ == "__main__":

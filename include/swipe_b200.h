@@ -311,6 +311,11 @@ int64_t swb_topk_merge(int nshards, const int64_t *const *scores, const int64_t 
                        int64_t *totalhits, int64_t *obvious);
 
 /* ---- tuning / introspection (not part of the reference's surface) -------------------------- */
+/* Measured issue rate of the packed 16x2 DPX instructions (VIADDMNMX / VIMNMX3) the scan is bound by,
+ * in warp instructions per clock per SM, and the SM clock the measurement ran at.  A DP cell pair
+ * costs 3.5 of them, so rate * 64 / 3.5 cells per clock per SM is the scan's integer-issue ceiling on
+ * this device -- the roofline denominator bench.py reports (calibrated by microbenchmark). */
+int swb_alu_peak(int device, double *dpx_per_clk_per_sm, double *sm_clock_mhz);
 /* Forces every subject through one kernel family: 0 = cascade (default), 1 = packed 16-bit
  * lanes only is not allowed (would not be exact) -> rejected; 2 = wide kernel for everything.  */
 int swb_set_mode(swb_db *db, int mode);

@@ -5,6 +5,6 @@ this package is the thin host-side binding used by the tests and bench.py.  Ther
 implementation here: every compute call goes to the CUDA library and fails loudly without it.
 """
 from .api import (Database, Scoring, SwbError, load_library, topk_merge, device_count,  # noqa: F401
-                  HostBuffer, BlastDB, align, hits_merge, set_cache_limit)
+                  HostBuffer, BlastDB, align, hits_merge, set_cache_limit, alu_peak)
 from .scoring import (blosum62, nucleotide_matrix, parse_matrix, matrix_limits,  # noqa: F401
                       encode_protein, encode_nucleotide, SYM_AA, SYM_NT16)

@@ -12,7 +12,7 @@ STATUS = {0: "SWB_OK", -1: "SWB_ERR_ARG", -2: "SWB_ERR_NO_DEVICE", -3: "SWB_ERR_
           -4: "SWB_ERR_NOMEM", -5: "SWB_ERR_RANGE", -6: "SWB_ERR_INTERNAL", -7: "SWB_ERR_IO"}
 
 # every symbol include/swipe_b200.h declares (tests check the library exports all of them)
-EXPORTS = ["swb_abi_version", "swb_align", "swb_blastdb_close", "swb_blastdb_date",
+EXPORTS = ["swb_abi_version", "swb_align", "swb_alu_peak", "swb_blastdb_close", "swb_blastdb_date",
            "swb_blastdb_error", "swb_blastdb_header", "swb_blastdb_included", "swb_blastdb_info",
            "swb_blastdb_masked_info", "swb_blastdb_open", "swb_blastdb_seqlen", "swb_blastdb_sequence",
            "swb_blastdb_title", "swb_db_close", "swb_db_info", "swb_db_open",
@@ -92,6 +92,8 @@ def load_library():
     lib.swb_hits_merge.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), p64, C.c_int64,
                                    C.c_void_p, C.c_void_p]
     lib.swb_set_cache_limit.restype = C.c_int
+    lib.swb_alu_peak.restype = C.c_int
+    lib.swb_alu_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.swb_set_cache_limit.argtypes = [C.c_int64]
     lib.swb_topk_merge.restype = C.c_int64
     lib.swb_topk_merge.argtypes = [C.c_int, C.POINTER(C.c_void_p), p64, p64, C.c_int64, C.c_int64,
@@ -429,3 +431,10 @@ def hits_merge(lists, keep):
 
 def set_cache_limit(nbytes):
     _check(load_library().swb_set_cache_limit(int(nbytes)))
+
+
+def alu_peak(device=0):
+    """swb_alu_peak: (DPX warp instructions per clock per SM, SM clock in MHz during the measurement)."""
+    a, b = C.c_double(), C.c_double()
+    _check(load_library().swb_alu_peak(int(device), C.byref(a), C.byref(b)))
+    return a.value, b.value

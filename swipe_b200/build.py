@@ -7,8 +7,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "swipe_b200", "csrc")
 LIB = os.path.join(CSRC, "libswipe_b200.so")
-SOURCES = ["swb_api.cu", "swb_blastdb.cu", "swb_align.cu", "swb_scoring.cu", "swb_text.cu"]
-DEPS = ["swb_api.cu", "sw_kernels.cuh", "swb_blastdb.cu", "swb_blastdb.h", "swb_align.cu", "swb_scoring.cu", "swb_text.cu", "swb_tables.inc", os.path.join(ROOT, "include", "swipe_b200.h")]
+SOURCES = ["swb_api.cu", "swb_blastdb.cu", "swb_align.cu", "swb_scoring.cu", "swb_text.cu", "swb_ubench.cu"]
+DEPS = ["swb_api.cu", "sw_kernels.cuh", "swb_blastdb.cu", "swb_blastdb.h", "swb_align.cu", "swb_scoring.cu", "swb_text.cu", "swb_ubench.cu", "swb_tables.inc", os.path.join(ROOT, "include", "swipe_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -90,6 +90,28 @@ def dna_db(nseq, seed=20261020, min_len=150, max_len=250):
     return residues, offsets
 
 
+def dna_db_planted(nseq, query, seed=20261020, plant_every=1000, ambiguity_every=0):
+    """dna_db with a mutated (5 %) copy of a query window in every plant_every-th read, forward and
+    reverse-complemented in turn, and -- every ambiguity_every-th planted read -- a run of N (code 15)
+    inside it (the DNA workload of BASELINE configs[3])."""
+    residues, offsets = dna_db(nseq, seed=seed)
+    q = np.asarray(query, dtype=np.uint8)
+    rng = np.random.default_rng(seed + 24)
+    lens = offsets[1:] - offsets[:-1]
+    for n, i in enumerate(range(0, nseq, plant_every)):
+        w = int(min(lens[i], 140, q.size))
+        s0 = int(rng.integers(0, q.size - w + 1))
+        piece = q[s0:s0 + w].copy()
+        if n % 2:
+            piece = revcomp_nt(piece)
+        mut = rng.random(w) < 0.05
+        piece[mut] = 1 << rng.integers(0, 4, size=int(mut.sum()))
+        if ambiguity_every and n % ambiguity_every == 0 and w > 20:
+            piece[10:14] = 15
+        residues[offsets[i]: offsets[i] + w] = piece
+    return residues, offsets
+
+
 def revcomp_nt(codes):
     """Reverse complement of one-hot/ambiguity nt codes: bit-reverse the 4-bit code
     (query.cc:112 ntcompl) and reverse the order."""

@@ -169,3 +169,85 @@ def write_fasta(path, codes, protein=True, name="query"):
         f.write(">%s\n" % name)
         for i in range(0, len(text), 60):
             f.write(text[i:i + 60] + "\n")
+
+
+# ---- vectorised writers for large synthetic databases (bench.py's reference arm, scale tests) -------
+def _fixed_headers(n):
+    """n deflines of identical size ('lcl|s%08d subject'): (bytes, offsets[n+1])."""
+    rec = np.frombuffer(_defline("s00000000", "subject"), dtype=np.uint8)
+    at = bytes(rec).index(b"s00000000") + 1
+    hdr = np.tile(rec, (n, 1))
+    idx = np.arange(n, dtype=np.int64)
+    for d in range(8):
+        hdr[:, at + 7 - d] = 48 + (idx // 10 ** d) % 10
+    return hdr.reshape(-1), np.arange(n + 1, dtype=np.int64) * rec.size
+
+
+def write_protein_fast(basename, residues, offsets, title="synthetic protein db",
+                       date="Oct 17, 2026  5:00 AM"):
+    """Like write_protein for (residues, offsets) arrays of millions of subjects."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    total = int(offsets[-1] - offsets[0])
+    res = np.asarray(residues, dtype=np.uint8)[offsets[0]: offsets[-1]]
+    psq = np.zeros(total + n + 1, dtype=np.uint8)
+    keep = np.ones(total + n + 1, dtype=bool)
+    keep[(offsets - offsets[0]) + np.arange(n + 1)] = False        # the NUL before / after every subject
+    psq[keep] = res
+    soff = (offsets - offsets[0]) + np.arange(n + 1) + 1
+    hdr, hoff = _fixed_headers(n)
+    lens = offsets[1:] - offsets[:-1]
+    _index(basename + ".pin", True, title, date, n, total, int(lens.max()) if n else 0, [hoff, soff])
+    psq.tofile(basename + ".psq")
+    hdr.tofile(basename + ".phr")
+    return soff
+
+
+def write_nucleotide_fast(basename, residues, offsets, title="synthetic nt db",
+                          date="Oct 17, 2026  5:00 AM", chunk=500_000):
+    """Like write_nucleotide for millions of short reads: 2-bit packing vectorised over chunks of
+    reads; the few reads holding ambiguity codes get their table through pack_nt."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    res = np.asarray(residues, dtype=np.uint8)
+    lens = offsets[1:] - offsets[:-1]
+    plen = lens // 4 + 1
+    pieces = [np.zeros(1, dtype=np.uint8)]
+    tails = {}
+    for c0 in range(0, n, chunk):
+        c1 = min(n, c0 + chunk)
+        L = lens[c0:c1]
+        width = int(-(-int(L.max()) // 4) * 4 + 4)
+        seg = res[offsets[c0]: offsets[c1]]
+        amb = ~np.isin(seg, [1, 2, 4, 8])
+        if amb.any():
+            rid = np.unique(np.searchsorted(offsets[c0: c1 + 1], np.nonzero(amb)[0] + offsets[c0],
+                                            side="right") - 1) + c0
+            for r in rid:
+                tails[int(r)] = pack_nt(res[offsets[r]: offsets[r + 1]])[1]
+        grid = np.zeros((c1 - c0, width), dtype=np.uint8)
+        grid[np.arange(width)[None, :] < L[:, None]] = _TWOBIT[seg & 15]
+        by = (grid[:, 0::4] << 6) | (grid[:, 1::4] << 4) | (grid[:, 2::4] << 2) | grid[:, 3::4]
+        by[np.arange(c1 - c0), L // 4] |= (L % 4).astype(np.uint8)
+        pieces.append(by[np.arange(width // 4)[None, :] < plen[c0:c1, None]])
+    sq = np.concatenate(pieces)
+    soff = np.ones(n + 1, dtype=np.int64)
+    soff[1:] += np.cumsum(plen)
+    aoff = soff[1:].copy()                                  # no table: the next record follows the packed bases
+    if tails:
+        rid = np.array(sorted(tails), dtype=np.int64)
+        tl = np.array([len(tails[int(r)]) for r in rid], dtype=np.int64)
+        sq = np.insert(sq, np.repeat(soff[rid + 1], tl),
+                       np.frombuffer(b"".join(tails[int(r)] for r in rid), dtype=np.uint8))
+        shift = np.zeros(n + 1, dtype=np.int64)
+        shift[rid + 1] = tl
+        shift = np.cumsum(shift)
+        aoff = soff[1:] + shift[:-1]
+        soff = soff + shift
+    aoff_full = np.concatenate([aoff, soff[-1:]])
+    hdr, hoff = _fixed_headers(n)
+    _index(basename + ".nin", False, title, date, n, int(lens.sum()), int(lens.max()) if n else 0,
+           [hoff, soff, aoff_full])
+    sq.tofile(basename + ".nsq")
+    hdr.tofile(basename + ".nhr")
+    return soff, aoff_full

@@ -366,3 +366,78 @@ def test_list_with_repeated_subjects(oracle):
     with Database(residues, offsets) as db:
         got = db.search_list(q, Scoring(B62, 11, 1), sel)
     assert np.array_equal(got, exp[sel])
+
+
+def test_query_5000_auto_shape(oracle):
+    """BASELINE configs[2], longest query: the automatically chosen multi-pass shape (G32 x R20,
+    8 passes at 5000 rows) against the oracle, planted copies re-queueing to the 16-bit tier."""
+    q = synth.protein_query(5000, seed=20261017 + 5000)
+    residues, offsets = synth.protein_db(700, query=q, seed=5001, plant_every=25, max_len=1500)
+    with Database(residues, offsets) as db:
+        got, c = _check(db, q, Scoring(B62, 11, 1), oracle, residues, offsets, "qlen 5000")
+        assert c["gpu_requeued"] > 0          # some planted copies leave the 11-bit range
+        hseq, hsc, _, _ = db.search_hits(q, Scoring(B62, 11, 1), 50, 1)
+    oseq, osc, _, _ = oracle.topk(np.arange(got.size), got, 50, min_score=1)
+    assert np.array_equal(hseq, oseq) and np.array_equal(hsc, osc)
+
+
+_MP = {}
+
+
+def _mp_case(oracle):
+    if not _MP:
+        q = synth.protein_query(1100, seed=20261017 + 1100)
+        residues, offsets = synth.protein_db(500, query=q, seed=1101, plant_every=20, max_len=1400)
+        exp, _, _ = oracle.scan(residues, offsets, q, B62, 11, 1)
+        _MP.update(q=q, residues=residues, offsets=offsets, exp=exp)
+    return _MP
+
+
+SHAPES = [(8, 8), (8, 13), (8, 16), (16, 12), (16, 16), (16, 20), (16, 24), (32, 12), (32, 16),
+          (32, 20), (32, 24), (32, 28), (32, 32)]
+
+
+@pytest.mark.parametrize("G,R", SHAPES)
+def test_every_shape_multi_pass(oracle, G, R):
+    """Every compiled scan shape in multi-pass mode (1100 rows > G * R for all of them), both lane
+    arithmetics, default penalties (immediate builds) and non-default ones (generic builds)."""
+    case = _mp_case(oracle)
+    with Database(case["residues"], case["offsets"]) as db:
+        for lane_mode in (1, 0):
+            db.set_shape(G, R, lane_mode)
+            got = db.search(case["q"], Scoring(B62, 11, 1))
+            assert np.array_equal(got, case["exp"]), "G%d R%d mode %d" % (G, R, lane_mode)
+        db.set_shape(G, R, 1)
+        got = db.search(case["q"], Scoring(B62, 9, 2))
+        exp, _, _ = oracle.scan(case["residues"], case["offsets"], case["q"], B62, 9, 2)
+        assert np.array_equal(got, exp), "G%d R%d generic penalties" % (G, R)
+
+
+def test_nucleotide_one_million_reads_vs_reference():
+    """BASELINE configs[3] at 1/50 of its size: 1 M reads (200 M nt), 1000-nt query, +1/-3, gaps 5/2,
+    both strands, against the UNMODIFIED reference kernels (oracle/_ref: search7 -> search16 ->
+    fullsw) where they are built, else the C oracle."""
+    import os
+    import oracle_lib
+    q = synth.dna_query(1000)
+    residues, offsets = synth.dna_db_planted(1_000_000, q, seed=31, plant_every=500, ambiguity_every=7)
+    m = scoring.nucleotide_matrix(1, -3)
+    threads = os.cpu_count() or 1
+    if oracle_lib.ref_available():
+        ref = oracle_lib.Ref()
+        ref.matrix_init("x", symtype=0, match=1, mismatch=-3)
+
+        def cpu(qq):
+            return ref.scan(residues, offsets, qq, 5, 2, threads=threads, chunk=4096, ssse3=1)[0]
+    else:
+        orc = oracle_lib.Oracle()
+
+        def cpu(qq):
+            return orc.scan(residues, offsets, qq, m, 5, 2, threads=threads)[0]
+    with Database(residues, offsets) as db:
+        for name, qq in (("plus", q), ("minus", synth.revcomp_nt(q))):
+            got = db.search(qq, Scoring(m, 5, 2))
+            exp = cpu(qq)
+            bad = np.nonzero(got != exp)[0]
+            assert bad.size == 0, "%s strand: %d scores differ, first %s" % (name, bad.size, bad[:5])
+            assert got.max() > 100                      # the planted copies are found
