@@ -325,6 +325,10 @@ int swb_db_open_ms(const swb_db *db, double *upload_ms, double *layout_ms);
 /* Test hook: pin the scan kernel shape (G threads per stream, R query rows per thread) and the
  * lane arithmetic (0 = DPX int16 only, 1 = DPX + fp16-pattern adds); (0, 0, -1) = automatic.   */
 int swb_set_shape(swb_db *db, int G, int R, int lane_mode);
+/* Test hook: which scan kernel geometry may be chosen: 1 = a warp holds four pipeline stages of eight
+ * streams (swb_scan_kernel), 2 = a warp is one stage of 32 streams (swb_scan2_kernel), 0 = automatic.
+ * Call before swb_set_shape when both are used.                                                  */
+int swb_set_geometry(swb_db *db, int geometry);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ EXPORTS = ["swb_abi_version", "swb_align", "swb_alu_peak", "swb_blastdb_close", 
            "swb_matrix_limits", "swb_matrix_nucleotide", "swb_matrix_parse", "swb_matrix_read",
            "swb_matrix_read_sound", "swb_query_parse", "swb_revcomp", "swb_search",
            "swb_search_end", "swb_search_hits", "swb_search_list", "swb_set_cache_limit",
-           "swb_hits_merge", "swb_set_mode", "swb_set_shape",
+           "swb_hits_merge", "swb_set_geometry", "swb_set_mode", "swb_set_shape",
            "swb_stats_bits", "swb_stats_default_gaps", "swb_stats_evalue", "swb_stats_init",
            "swb_stats_length_adjustment", "swb_stats_params", "swb_stats_params_nt", "swb_strerror",
            "swb_topk_merge", "swb_translate", "swb_translate_table", "swb_trim"]
@@ -101,6 +101,8 @@ def load_library():
     lib.swb_set_mode.argtypes = [C.c_void_p, C.c_int]
     lib.swb_db_open_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.swb_set_shape.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.swb_set_geometry.argtypes = [C.c_void_p, C.c_int]
+    lib.swb_set_geometry.restype = C.c_int
     for name in ("swb_device_count", "swb_host_alloc", "swb_host_free", "swb_db_open",
                  "swb_db_close", "swb_db_info", "swb_search", "swb_search_list", "swb_search_end",
                  "swb_set_mode", "swb_db_open_ms", "swb_set_shape", "swb_db_open_async", "swb_db_wait"):
@@ -317,6 +319,9 @@ class Database:
 
     def set_mode(self, mode):
         _check(self._lib.swb_set_mode(self._h, int(mode)))
+
+    def set_geometry(self, geometry=0):
+        _check(self._lib.swb_set_geometry(self._h, int(geometry)))
 
     def set_shape(self, G=0, R=0, lane_mode=-1):
         _check(self._lib.swb_set_shape(self._h, int(G), int(R), int(lane_mode)))

@@ -170,6 +170,34 @@ __device__ __forceinline__ void swb_cell(u32 hd, u32 s, u32 &e, u32 &f, u32 &h, 
   }
 }
 
+// The same cell in two halves, for loops that want the first operation of a cell issued early (it only
+// needs the diagonal value, the score and -- in the int16 build -- E, all known before the cell's turn):
+// a = swb_cell_pre(hd, s, e), then swb_cell_post(a, e, f, h, smax).
+template <int MODE> __device__ __forceinline__ u32 swb_cell_pre(u32 hd, u32 s, u32 e)
+{
+  return MODE == SWB_MODE_INT16 ? __viaddmax_s16x2(hd, s, e) : swb_hadd2(hd, s);
+}
+template <int MODE>
+__device__ __forceinline__ void swb_cell_post(u32 a, u32 &e, u32 &f, u32 &h, u32 &smax, const u32 negq, const u32 negr)
+{
+  if (MODE == SWB_MODE_INT16)
+  {
+    h = __vimax_s16x2_relu(a, f);
+    smax = __vmaxs2(smax, h);
+    const u32 hq = __vadd2(h, negq);
+    e = __viaddmax_s16x2(e, negr, hq);
+    f = __viaddmax_s16x2(f, negr, hq);
+  }
+  else
+  {
+    h = __vimax3_s16x2_relu(a, e, f);
+    smax = __vmaxs2(smax, h);
+    const u32 hq = swb_hadd2(h, negq);
+    e = __viaddmax_s16x2_relu(e, negr, hq);
+    f = __viaddmax_s16x2_relu(f, negr, hq);
+  }
+}
+
 // Shared-memory geometry of the scan kernel (host and device agree through these).
 #define SWB_STREAMS 8                        // streams per CTA = threads per quarter-warp
 #define SWB_MS_STRIDE 34                     // halfwords per subject code in the staged score matrix
@@ -409,6 +437,252 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       roff = roff + slot_bytes == ring_bytes ? 0u : roff + slot_bytes;
       xin ^= xin_toggle;
       xout ^= xout_toggle;
+      b++;
+    }
+  }
+}
+
+// ---- scan kernel, second geometry: one warp = one pipeline stage of 32 streams -----------------------
+// Same systolic scan, same tables, same block stream; what changes is who sits where.  In
+// swb_scan_kernel a warp holds four consecutive stages of eight streams, so its four quarter-warps
+// read four different ring slots and every LDS.128 of the inner loop needs a per-thread address add.
+// Here a CTA is G warps x 32 streams and warp g IS stage g: ring slot, mailbox and query-row offsets
+// are warp-uniform, the ring offset rides in a uniform register of the LDS ([R + UR]) and costs no
+// instruction, every hand-off goes through a shared-memory mailbox (three LDS + three STS per step
+// instead of nine shuffles), and the START / END flags of a block travel down the pipeline in the two
+// spare sign bits of the running-maximum word instead of a table row of their own.  One CTA of 32 G
+// threads per SM (G = 16: 512 threads at 128 registers, the whole register file).
+// Shared memory: header | ring [G+1][nq+1][32 streams][16 B] | mailboxes [G][2][H 512 B | F 512 B | S 128 B];
+// mailbox g is the INPUT of stage g (mailbox 0: zeros, or the previous pass's bottom row, which
+// cp.async brings in one step ahead so that the load latency never stalls the pipeline).
+#define SWB2_STREAMS 32
+#define SWB2_XFER 1152                       // one mailbox, one parity
+#define SWB2_FLAG_START 0x00008000u          // in the running-maximum word of a mailbox
+#define SWB2_FLAG_END 0x80000000u
+__host__ __device__ inline int swb_scan2_threads(int G) { return SWB2_STREAMS * G; }
+__host__ __device__ inline size_t swb_scan2_smem(int G, int nq)
+{
+  return SWB_SMEM_HEADER + (size_t)(G + 1) * (nq + 1) * 512 + (size_t)G * 2 * SWB2_XFER;
+}
+
+__device__ __forceinline__ void swb_cp_async16(u32 dst, const void *src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+
+template <int G, int R, int MODE, bool MP, u32 KQ = 0, u32 KR = 0>
+__global__ void __launch_bounds__(SWB2_STREAMS * G, 16 / G) swb_scan2_kernel(const ScanParams P)
+{
+  extern __shared__ uint4 smem4[];
+  const u32 sbase = (u32)__cvta_generic_to_shared(smem4);     // staged score matrix at sbase
+  constexpr int NSLOT = G + 1;
+  constexpr int RG = G >= 4 ? G / 4 : 1;              // row groups of the table build
+  constexpr int NBJ = (32 + RG - 1) / RG;             // rows one thread may have to build
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int g = __shfl_sync(0xffffffffu, tid >> 5, 0);        // stage = warp, known to be warp-uniform
+  const int nq = P.nq;
+  const u32 slot_bytes = (u32)(nq + 1) * 512u;
+  const u32 ring = sbase + SWB_SMEM_HEADER;
+  const u32 ring_bytes = (u32)NSLOT * slot_bytes;
+  const u32 xfer = ring + ring_bytes;
+
+  __shared__ __align__(8) unsigned long long tma_bar;
+  const u32 bar = (u32)__cvta_generic_to_shared(&tma_bar);
+  if (tid == 0)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((u32)SWB_M16_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sbase), "l"(__cvta_generic_to_global(P.m16)), "r"((u32)SWB_M16_BYTES), "r"(bar) : "memory");
+  }
+  // the pad row of every slot is written once and never rebuilt; mailbox 0 starts out all zero
+  for (int i = tid; i < NSLOT * SWB2_STREAMS; i += blockDim.x)
+    swb_sts128(ring + (u32)(i >> 5) * slot_bytes + (u32)nq * 512u + (u32)(i & 31) * 16u,
+               make_uint4(P.padword, P.padword, P.padword, P.padword));
+  for (int i = tid; i < 2 * SWB2_XFER / 4; i += blockDim.x) swb_sts32(xfer + 4u * i, 0);
+  __syncthreads();
+  {
+    u32 done = 0;
+    for (int spins = 0; !done; spins++)
+    {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar) : "memory");
+      if (spins > (1 << 24)) __trap();
+    }
+  }
+
+  ScanSeg S = P.seg;
+  if (P.segs) S = P.segs[blockIdx.y];
+  const int stream = blockIdx.x * SWB2_STREAMS + lane;
+  const int p0 = S.stream_pair[stream];
+  const int p1 = S.stream_pair[stream + 1];
+  const long long b0 = S.pairblk[p0];
+  const int nblk = (int)(S.pairblk[p1] - b0);
+  const uint2 *blk = S.blocks + b0;
+  const long long bnd0 = S.bnd_base + b0;
+  const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);   // every warp holds all 32 streams
+  const int nsteps = nblk_max > 0 ? nblk_max + G - 1 : 0;
+  const u32 negq = (KQ | KR) ? KQ : P.negq, negr = (KQ | KR) ? KR : P.negr;
+  // table build: this thread fills ONE column of its stream's table, rows brow, brow + RG, ...; the
+  // column rotates with the lane's octet so that the 32 STS.32 of a warp fall into 32 different banks
+  const int bcol = ((lane >> 3) + g) & 3;
+  const int brow = G >= 4 ? g >> 2 : 0;
+  const u32 bshift = 8u * (u32)bcol;
+  const u32 bdst = ring + (u32)lane * 16u + (u32)bcol * 4u + (u32)brow * 512u;
+  const u32 bsrc = sbase + 2u * (u32)brow;
+  const u32 lane16 = (u32)lane * 16u;
+  const u32 xin0 = xfer + (u32)g * (2u * SWB2_XFER) + lane16;          // input mailbox, parity 0
+  const u32 xout0 = xin0 + 2u * SWB2_XFER;                             // = input mailbox of stage g + 1
+  const u32 xs0 = xin0 - lane16 + 1024u + (u32)lane * 4u;              // running maximum + flags word of the input
+
+  u32 bmask = 0;                                     // bit j: this thread builds row brow + j * RG
+#pragma unroll
+  for (int j = 0; j < NBJ; j++)
+    if (brow + j * RG < nq) bmask |= 1u << j;
+  auto build = [&](const uint2 blkw, const u32 slot_off, const bool on) {
+    const u32 da = bsrc + ((blkw.x >> bshift) & 63u) * (2u * SWB_MS_STRIDE);
+    const u32 db = bsrc + ((blkw.y >> bshift) & 63u) * (2u * SWB_MS_STRIDE);
+    const u32 dst = bdst + slot_off;
+    const u32 bm = on ? bmask : 0u;
+#pragma unroll
+    for (int j = 0; j < NBJ; j++)
+      if (bm & (1u << j))
+        swb_sts32(dst + j * RG * 512, swb_pack16(swb_lds16(da + j * RG * 2), swb_lds16(db + j * RG * 2)));
+  };
+
+  const int npass = MP ? P.npass : 1;
+  for (int pass = 0; pass < npass; pass++)
+  {
+    u32 rq[R];
+#pragma unroll
+    for (int i = 0; i < R; i++)
+      rq[i] = ring + (u32)P.qrow_off[(pass * G + g) * R + i] * 32u + lane16;
+
+    u32 H[R], E[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) { H[i] = 0; E[i] = 0; }
+    u32 smax = 0, dtop = 0;
+    int pair_out = p0;
+    const bool feed = MP && (pass > 0) && (g == 0);    // stage 0 reads the previous pass's bottom row
+    const bool spill = MP && (pass + 1 < npass) && (g == G - 1);
+
+    if (MP && pass > 0) __syncthreads();               // the previous pass is done with ring and mailboxes
+    uint2 now = make_uint2(0, 0), nxt = make_uint2(0, 0);     // blocks t and t + 1
+    if (nblk > 0) { now = swb_ldg_blk(blk); build(now, 0, true); }
+    if (nblk > 1) nxt = swb_ldg_blk(blk + 1);
+    if (MP && feed)
+    {
+      if (nblk > 0)
+      {
+        swb_cp_async16(xin0, P.bndH + bnd0);            // block 0's top row -> parity 0
+        swb_cp_async16(xin0 + 512u, P.bndF + bnd0);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const uint2 *pnext = blk + 2;
+    u32 woff = slot_bytes;                             // ((t + 1) % NSLOT) * slot_bytes
+    u32 roff = (u32)((NSLOT - g) % NSLOT) * slot_bytes;  // ((t - g) mod NSLOT) * slot_bytes
+    u32 par = 0;                                       // (t & 1) * SWB2_XFER
+    int b = -g;
+
+    for (int t = 0; t < nsteps; t++)
+    {
+      if (MP && feed) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      // ---- tables of block t + 1 (first read after the next barrier) ------------------------------
+      const uint2 cur = nxt;
+      if (t + 2 < nblk) nxt = swb_ldg_blk(pnext);
+      pnext++;
+      build(cur, woff, t + 1 < nblk);
+      if (MP && feed)
+      {
+        if (t + 1 < nblk)                              // top row of block t + 1 -> the other parity
+        {
+          swb_cp_async16(xin0 + (par ^ SWB2_XFER), P.bndH + bnd0 + t + 1);
+          swb_cp_async16(xin0 + (par ^ SWB2_XFER) + 512u, P.bndF + bnd0 + t + 1);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+
+      // ---- stage g works on block b = t - g ----------------------------------------------------------
+      const bool active = b >= 0 && b < nblk;
+      const uint4 vh = swb_lds128(xin0 + par), vf = swb_lds128(xin0 + par + 512u);
+      u32 is;
+      if (g == 0) is = ((now.x >> 6) & 1u) * SWB2_FLAG_START + ((now.x >> 7) & 1u) * SWB2_FLAG_END;
+      else is = swb_lds32(xs0 + par);
+      if (is & SWB2_FLAG_START)
+      {
+#pragma unroll
+        for (int i = 0; i < R; i++) { H[i] = 0; E[i] = 0; }
+        smax = 0;
+        dtop = 0;
+      }
+      const u32 flagbits = is & (SWB2_FLAG_START | SWB2_FLAG_END);
+      smax = __vmaxs2(smax, is & ~(SWB2_FLAG_START | SWB2_FLAG_END));
+      u32 hup0 = vh.x, hup1 = vh.y, hup2 = vh.z, hup3 = vh.w;
+      u32 f0 = vf.x, f1 = vf.y, f2 = vf.z, f3 = vf.w;
+      // H[i] holds H(row i, last column of the previous block) = the diagonal input of row i + 1.  It is
+      // consumed by the first operation of row i + 1's first cell, issued one row EARLY (software
+      // pipelining of the score load and that operation), so that the register is free again when row
+      // i's own last column is written back into it.
+      uint4 sc = swb_lds128(rq[0] + roff);
+      u32 a0 = swb_cell_pre<MODE>(dtop, sc.x, E[0]);
+      dtop = vh.w;
+#pragma unroll
+      for (int i = 0; i < R; i++)
+      {
+        uint4 scn = sc;
+        u32 an = 0;
+        if (i + 1 < R)
+        {
+          scn = swb_lds128(rq[i + 1] + roff);
+          an = swb_cell_pre<MODE>(H[i], scn.x, E[i + 1]);
+        }
+        u32 e = E[i], h, a;
+        swb_cell_post<MODE>(a0, e, f0, h, smax, negq, negr);
+        a = swb_cell_pre<MODE>(hup0, sc.y, e); hup0 = h;
+        swb_cell_post<MODE>(a, e, f1, h, smax, negq, negr);
+        a = swb_cell_pre<MODE>(hup1, sc.z, e); hup1 = h;
+        swb_cell_post<MODE>(a, e, f2, h, smax, negq, negr);
+        a = swb_cell_pre<MODE>(hup2, sc.w, e); hup2 = h;
+        swb_cell_post<MODE>(a, e, f3, h, smax, negq, negr);
+        hup3 = h;
+        H[i] = h;
+        E[i] = e;
+        sc = scn;
+        a0 = an;
+      }
+      if (g == G - 1)
+      {
+        if (MP && spill && active)
+        {
+          P.bndH[bnd0 + b] = make_uint4(hup0, hup1, hup2, hup3);
+          P.bndF[bnd0 + b] = make_uint4(f0, f1, f2, f3);
+        }
+        if (active && (flagbits & SWB2_FLAG_END))
+        {
+          u32 v = smax;
+          if (MP && pass > 0) v = __vmaxs2(v, S.pair_scores[pair_out]);
+          S.pair_scores[pair_out] = v;
+          pair_out++;
+        }
+      }
+      else
+      {
+        // ---- hand the strip's bottom row to the next stage ------------------------------------------
+        // (written to the parity the next stage reads at step t + 1; it is reading the other one now)
+        const u32 wpar = par ^ SWB2_XFER;
+        swb_sts128(xout0 + wpar, make_uint4(hup0, hup1, hup2, hup3));
+        swb_sts128(xout0 + wpar + 512u, make_uint4(f0, f1, f2, f3));
+        swb_sts32(xs0 + 2u * SWB2_XFER + wpar, smax | flagbits);
+      }
+      now = cur;
+      woff = woff + slot_bytes == ring_bytes ? 0u : woff + slot_bytes;
+      roff = roff + slot_bytes == ring_bytes ? 0u : roff + slot_bytes;
+      par ^= SWB2_XFER;
       b++;
     }
   }

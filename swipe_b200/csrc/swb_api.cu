@@ -242,6 +242,7 @@ struct swb_db
   cudaEvent_t ev_group[2] = {nullptr, nullptr};   // completion of the last two scan launches
   double upload_ms = 0, layout_ms = 0;
   int force_G = 0, force_R = 0, force_mode = -1;   // test hooks (swb_set_shape)
+  int force_geom = 0;                              // 0 = automatic, 1 / 2 = scan kernel geometry (swb_set_geometry)
 };
 
 namespace
@@ -331,8 +332,10 @@ inline short enc16(long long v, int mode)
   return (short)v;
 }
 
+// pad_after: table rows between the last symbol row and the padding row (geometry 1 keeps a row of
+// START / END flags there, geometry 2 does not)
 int prepare_tables(Tables &t, const unsigned char *query, long long qlen, const swb_scoring *sc,
-                   int mode, int rows_padded)
+                   int mode, int rows_padded, int pad_after = 1)
 {
   for (int i = 0; i < 32; i++) t.rowof[i] = -1;
   t.nq = 0;
@@ -363,7 +366,7 @@ int prepare_tables(Tables &t, const unsigned char *query, long long qlen, const 
           if (t.rowof[qs] == s) v = sc->matrix[(d << 5) + qs];
       t.m16[d * SWB_MS_STRIDE + s] = t.narrow_ok ? enc16(v, mode) : (short)0;
     }
-  t.qrow.assign((size_t)rows_padded, (unsigned short)((t.nq + 1) * 16));
+  t.qrow.assign((size_t)rows_padded, (unsigned short)((t.nq + pad_after) * 16));
   for (long long i = 0; i < qlen && i < rows_padded; i++)
     t.qrow[(size_t)i] = (unsigned short)(t.rowof[query[i]] * 16);
   return SWB_OK;
@@ -371,27 +374,31 @@ int prepare_tables(Tables &t, const unsigned char *query, long long qlen, const 
 
 // ---- kernel shapes -----------------------------------------------------------------------------
 typedef void (*scan_fn)(const ScanParams);
-struct ShapeEntry { int G, R, mode; scan_fn fn, fn_mp; u32 kq, kr; };   // single-pass / multi-pass builds
+struct ShapeEntry { int G, R, mode; scan_fn fn, fn_mp; u32 kq, kr; int geom; };   // single-pass / multi-pass builds
 
 // hybrid-mode encodings of the two default scoring systems' penalties, compiled in as immediates:
 // BLOSUM62 11+1k (open+extend 12, extend 1) and nucleotide 5+2k (7, 2)
 #define SWB_KQ(q) (0x8000u | (q)) | ((0x8000u | (q)) << 16)
 #define SWB_KR(r) ((0x10000u - (r)) | ((0x10000u - (r)) << 16))
 
-#define SWB_SHAPE(G, R)                                                                          \
-  {G, R, SWB_MODE_INT16, swb_scan_kernel<G, R, SWB_MODE_INT16, false>,                           \
-   swb_scan_kernel<G, R, SWB_MODE_INT16, true>, 0, 0},                                           \
-  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID, false>,                         \
-   swb_scan_kernel<G, R, SWB_MODE_HYBRID, true>, 0, 0},                                          \
-  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID, false, SWB_KQ(12), SWB_KR(1)>,  \
-   swb_scan_kernel<G, R, SWB_MODE_HYBRID, true, SWB_KQ(12), SWB_KR(1)>, SWB_KQ(12), SWB_KR(1)},  \
-  {G, R, SWB_MODE_HYBRID, swb_scan_kernel<G, R, SWB_MODE_HYBRID, false, SWB_KQ(7), SWB_KR(2)>,   \
-   swb_scan_kernel<G, R, SWB_MODE_HYBRID, true, SWB_KQ(7), SWB_KR(2)>, SWB_KQ(7), SWB_KR(2)}
+#define SWB_SHAPE_OF(KERNEL, GEOM, G, R)                                                         \
+  {G, R, SWB_MODE_INT16, KERNEL<G, R, SWB_MODE_INT16, false>,                                    \
+   KERNEL<G, R, SWB_MODE_INT16, true>, 0, 0, GEOM},                                              \
+  {G, R, SWB_MODE_HYBRID, KERNEL<G, R, SWB_MODE_HYBRID, false>,                                  \
+   KERNEL<G, R, SWB_MODE_HYBRID, true>, 0, 0, GEOM},                                             \
+  {G, R, SWB_MODE_HYBRID, KERNEL<G, R, SWB_MODE_HYBRID, false, SWB_KQ(12), SWB_KR(1)>,           \
+   KERNEL<G, R, SWB_MODE_HYBRID, true, SWB_KQ(12), SWB_KR(1)>, SWB_KQ(12), SWB_KR(1), GEOM},     \
+  {G, R, SWB_MODE_HYBRID, KERNEL<G, R, SWB_MODE_HYBRID, false, SWB_KQ(7), SWB_KR(2)>,            \
+   KERNEL<G, R, SWB_MODE_HYBRID, true, SWB_KQ(7), SWB_KR(2)>, SWB_KQ(7), SWB_KR(2), GEOM}
+#define SWB_SHAPE(G, R) SWB_SHAPE_OF(swb_scan_kernel, 1, G, R)
+#define SWB_SHAPE2(G, R) SWB_SHAPE_OF(swb_scan2_kernel, 2, G, R)
 
 const ShapeEntry g_shapes[] = {
     SWB_SHAPE(8, 8),   SWB_SHAPE(8, 13),  SWB_SHAPE(8, 16),  SWB_SHAPE(16, 12), SWB_SHAPE(16, 16),
     SWB_SHAPE(16, 20), SWB_SHAPE(16, 24), SWB_SHAPE(32, 12), SWB_SHAPE(32, 16), SWB_SHAPE(32, 20),
     SWB_SHAPE(32, 24), SWB_SHAPE(32, 28), SWB_SHAPE(32, 32),
+    // geometry 2 (one warp = one stage of 32 streams)
+    SWB_SHAPE2(16, 20), SWB_SHAPE2(16, 21), SWB_SHAPE2(16, 24), SWB_SHAPE2(4, 25),
 };
 const int g_nshapes = (int)(sizeof(g_shapes) / sizeof(g_shapes[0]));
 
@@ -399,21 +406,33 @@ const int g_nshapes = (int)(sizeof(g_shapes) / sizeof(g_shapes[0]));
 // Measured throughput of every compiled shape on padded rows (TCUPS of the hybrid build with the
 // penalties compiled in, 2 M-subject shard, tools/tune_shapes.py -> profiles/r1_tune_shapes.txt):
 // single pass / multi-pass.  Shapes without a multi-pass measurement use 0.93 x single pass.
-struct ShapeEff { int G, R; double sp, mp; };
+struct ShapeEff { int geom, G, R; double sp, mp; };
 const ShapeEff g_eff[] = {
-    {8, 8, 5.0, 0},     {8, 13, 5.52, 0},    {8, 16, 6.00, 0},    {16, 12, 6.42, 0},   {16, 16, 7.04, 0},
-    {16, 20, 7.09, 0},  {16, 24, 7.19, 6.18}, {32, 12, 6.36, 5.71}, {32, 16, 6.64, 6.44}, {32, 20, 6.80, 6.74},
-    {32, 24, 7.50, 6.45}, {32, 28, 7.39, 6.41}, {32, 32, 6.62, 6.38},
+    {1, 8, 8, 5.0, 0},     {1, 8, 13, 5.52, 0},    {1, 8, 16, 6.00, 0},    {1, 16, 12, 6.42, 0},   {1, 16, 16, 7.04, 0},
+    {1, 16, 20, 7.09, 0},  {1, 16, 24, 7.19, 6.18}, {1, 32, 12, 6.36, 5.71}, {1, 32, 16, 6.64, 6.44}, {1, 32, 20, 6.80, 6.74},
+    {1, 32, 24, 7.50, 6.45}, {1, 32, 28, 7.39, 6.41}, {1, 32, 32, 6.62, 6.38},
+    {2, 16, 20, 7.0, 6.8}, {2, 16, 21, 7.0, 6.8}, {2, 16, 24, 7.2, 6.9}, {2, 4, 25, 5.5, 5.0},
 };
 
 // (kq, kr): the penalties in the mode's packed encoding; a build with exactly these compiled in is
 // preferred over the generic one of the same shape (except where it measured slower).  The shape
 // that scores the query's rows fastest wins: efficiency x qlen / (passes x G x R).
-const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, u32 kq, u32 kr, int *npass)
+inline int shape_streams(const ShapeEntry &s) { return s.geom == 2 ? SWB2_STREAMS : SWB_STREAMS; }
+inline int shape_threads(const ShapeEntry &s) { return s.geom == 2 ? swb_scan2_threads(s.G) : swb_scan_threads(s.G); }
+inline size_t shape_smem(const ShapeEntry &s, int nq)
+{
+  return s.geom == 2 ? swb_scan2_smem(s.G, nq) : swb_scan_smem(s.G, nq);
+}
+const size_t SWB_SMEM_LIMIT = 227 * 1024;      // dynamic shared memory one CTA may ask for on sm_100
+
+const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, u32 kq, u32 kr, int *npass, int nq)
 {
   const ShapeEntry *best = nullptr;
   double best_rate = 0;
   const bool allow_spec = getenv("SWB_NO_SPEC") == nullptr;
+  int geom = db->force_geom;
+  if (geom == 0)
+    if (const char *env = getenv("SWB_GEOM")) geom = atoi(env);
   for (int i = 0; i < g_nshapes; i++)
   {
     const ShapeEntry &s = g_shapes[i];
@@ -421,13 +440,15 @@ const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, u32 k
     const bool spec = (s.kq | s.kr) != 0;
     if (spec && !(allow_spec && s.kq == kq && s.kr == kr)) continue;
     if (db->force_G && (s.G != db->force_G || s.R != db->force_R)) continue;
+    if (geom && s.geom != geom) continue;
+    if (shape_smem(s, nq) + 1024 > SWB_SMEM_LIMIT) continue;      // (+ the kernel's static shared memory)
     const long long rows = (long long)s.G * s.R;
     const long long np = std::max<long long>(1, (qlen + rows - 1) / rows);
     double eff = 5.0;
     for (const ShapeEff &e : g_eff)
-      if (e.G == s.G && e.R == s.R) eff = np > 1 ? (e.mp > 0 ? e.mp : 0.93 * e.sp) : e.sp;
+      if (e.G == s.G && e.R == s.R && e.geom == s.geom) eff = np > 1 ? (e.mp > 0 ? e.mp : 0.93 * e.sp) : e.sp;
     if (!spec) eff *= 0.955;                                   // generic builds read the penalties from registers
-    else if (s.G == 32 && s.R == 32 && np == 1) eff *= 0.87;   // this one spills with the immediates (5.60 vs 6.13)
+    else if (s.geom == 1 && s.G == 32 && s.R == 32 && np == 1) eff *= 0.87;   // this one spills with the immediates (5.60 vs 6.13)
     if (mode == SWB_MODE_INT16) eff *= 0.84;
     const double rate = eff * (double)std::max<long long>(qlen, 1) / (double)(np * rows);
     if (!best || rate > best_rate) { best = &s; best_rate = rate; *npass = (int)np; }
@@ -530,10 +551,16 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     kq = a | (a << 16);
     kr = b | (b << 16);
   }
-  const ShapeEntry *shape = choose_shape(db, qlen, mode, kq, kr, &npass);
+  int nq_probe = 0;
+  {
+    Tables probe;
+    SWB_TRY(prepare_tables(probe, query, qlen, sc, mode, 0));
+    nq_probe = probe.nq;
+  }
+  const ShapeEntry *shape = choose_shape(db, qlen, mode, kq, kr, &npass, nq_probe);
   if (!shape) return SWB_ERR_INTERNAL;
   const long long rows_padded = (long long)npass * shape->G * shape->R;
-  SWB_TRY(prepare_tables(tb, query, qlen, sc, mode, (int)rows_padded));
+  SWB_TRY(prepare_tables(tb, query, qlen, sc, mode, (int)rows_padded, shape->geom == 2 ? 0 : 1));
   const long long maxcell = std::max<long long>(tb.hi, 0) * std::min<long long>(qlen, db->longest);
   const bool use64 = maxcell + sc->gap_open_extend + 65536 > 0x7fffffffLL ||
                      sc->gap_open_extend > 0x3fffffff || sc->gap_extend > 0x3fffffff ||
@@ -586,8 +613,9 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       layouts = db->chunks;
     // launch geometry: one CTA = 8 streams x G stages; as many CTAs per SM as shared memory
     // and registers allow
-    const int threads = swb_scan_threads(shape->G);
-    const size_t smem = swb_scan_smem(shape->G, tb.nq);
+    const int threads = shape_threads(*shape);
+    const size_t smem = shape_smem(*shape, tb.nq);
+    const int cta_streams = shape_streams(*shape);
     const scan_fn fn = npass > 1 ? shape->fn_mp : shape->fn;
     SWB_CUDA(cudaFuncSetAttribute((const void *)fn,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -604,7 +632,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     if (const char *env = getenv("SWB_OVERSUB")) oversub = std::max(1, atoi(env));
     long long min_blocks = 0;
     for (Layout *L : layouts) min_blocks = std::max(min_blocks, L->cap_blocks);
-    while (oversub > 1 && min_blocks / ((long long)db->sm_count * occ * oversub * SWB_STREAMS) < 40 * shape->G)
+    while (oversub > 1 && min_blocks / ((long long)db->sm_count * occ * oversub * cta_streams) < 40 * shape->G)
       oversub--;                                   // keep streams much longer than the pipeline fill
     SWB_TRY(db->m16.reserve(SWB_M16_BYTES / sizeof(short)));
     SWB_TRY(db->qrow_off.reserve((size_t)rows_padded));
@@ -629,7 +657,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     (void)cudaGetLastError();
     if (merge && resident && !getenv("SWB_OVERSUB")) oversub = work.size() >= 4 ? 1 : oversub;
     const int grid = db->sm_count * occ * oversub;
-    const int nstreams = grid * SWB_STREAMS;
+    const int nstreams = grid * cta_streams;
     long long sum_blocks = 0;
     std::vector<ScanSeg> segs(work.size());
     for (size_t k = 0; k < work.size(); k++)
@@ -742,10 +770,10 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       // kernel.
       Tables t16;
       int np16 = 1;
-      const ShapeEntry *sh16 = choose_shape(db, qlen, SWB_MODE_INT16, 0, 0, &np16);
+      const ShapeEntry *sh16 = choose_shape(db, qlen, SWB_MODE_INT16, 0, 0, &np16, nq_probe);
       if (!sh16) return SWB_ERR_INTERNAL;
       const long long rows16 = (long long)np16 * sh16->G * sh16->R;
-      SWB_TRY(prepare_tables(t16, query, qlen, sc, SWB_MODE_INT16, (int)rows16));
+      SWB_TRY(prepare_tables(t16, query, qlen, sc, SWB_MODE_INT16, (int)rows16, sh16->geom == 2 ? 0 : 1));
       SWB_TRY(db->codes.reserve((size_t)nrequeue));
       SWB_TRY(db->requeue2.reserve((size_t)nrequeue));
       SWB_TRY(db->qrow_off.reserve((size_t)rows16));
@@ -760,8 +788,9 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       SWB_CUDA(cudaMemcpyAsync(db->qrow_off.p, t16.qrow.data(), t16.qrow.size() * sizeof(unsigned short),
                                cudaMemcpyHostToDevice, st));
       SWB_CUDA(cudaMemsetAsync(db->counters.p, 0, sizeof(unsigned long long), st));
-      const int threads16 = swb_scan_threads(sh16->G);
-      const size_t smem16 = swb_scan_smem(sh16->G, t16.nq);
+      const int threads16 = shape_threads(*sh16);
+      const size_t smem16 = shape_smem(*sh16, t16.nq);
+      const int streams16 = shape_streams(*sh16);
       const scan_fn fn16 = np16 > 1 ? sh16->fn_mp : sh16->fn;
       SWB_CUDA(cudaFuncSetAttribute((const void *)fn16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
       int occ16 = 0;
@@ -770,8 +799,8 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       // few subjects: no more streams than pairs (a stream walks its pairs one after the other)
       Layout &L2 = db->tmp2;
       int grid16 = db->sm_count * occ16;
-      grid16 = (int)std::max<long long>(1, std::min<long long>(grid16, (L2.npairs + SWB_STREAMS - 1) / SWB_STREAMS));
-      const int nstreams16 = grid16 * SWB_STREAMS;
+      grid16 = (int)std::max<long long>(1, std::min<long long>(grid16, (L2.npairs + streams16 - 1) / streams16));
+      const int nstreams16 = grid16 * streams16;
       SWB_TRY(L2.stream_pair.reserve((size_t)nstreams16 + 1));
       swb_partition_kernel<<<(nstreams16 + 1 + 255) / 256, 256, 0, st>>>(L2.pairblk.p, L2.npairs, nstreams16,
                                                                          L2.stream_pair.p);
@@ -1738,13 +1767,22 @@ int swb_db_open_ms(const swb_db *db, double *upload_ms, double *layout_ms)
 
 /* test hook: pin the scan kernel shape (G threads per stream, R rows per thread) and lane
    arithmetic (0 = int16 DPX only, 1 = DPX + fp16-pattern adds); zeros / -1 restore the default. */
+int swb_set_geometry(swb_db *db, int geometry)
+{
+  if (!db || geometry < 0 || geometry > 2) return SWB_ERR_ARG;
+  db->force_geom = geometry;
+  return SWB_OK;
+}
+
 int swb_set_shape(swb_db *db, int G, int R, int lane_mode)
 {
   if (!db) return SWB_ERR_ARG;
   if (G != 0)
   {
     bool found = false;
-    for (int i = 0; i < g_nshapes; i++) found = found || (g_shapes[i].G == G && g_shapes[i].R == R);
+    for (int i = 0; i < g_nshapes; i++)
+      found = found || (g_shapes[i].G == G && g_shapes[i].R == R &&
+                        (db->force_geom == 0 || g_shapes[i].geom == db->force_geom));
     if (!found) return SWB_ERR_ARG;
   }
   if (lane_mode < -1 || lane_mode > 1) return SWB_ERR_ARG;

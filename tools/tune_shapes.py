@@ -11,11 +11,13 @@ shapes = [(8, 8), (8, 13), (8, 16), (16, 12), (16, 16), (16, 20), (16, 24), (32,
 if len(sys.argv) > 3:
     shapes = [tuple(int(v) for v in x.split("x")) for x in sys.argv[3].split(",")]
 modes = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 0]
+geom = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 q0 = synth.protein_query(375)
 residues, offsets = synth.protein_db(nseq, query=q0)
 sc = Scoring(scoring.blosum62(), 11, 1)
 ref = None
 with Database(residues, offsets) as db:
+    db.set_geometry(geom)
     for qlen in qlens:
         q = synth.protein_query(qlen)
         cells = float(offsets[-1]) * qlen
@@ -23,7 +25,7 @@ with Database(residues, offsets) as db:
         for lane_mode in modes:
             for (G, R) in shapes:
                 npass = -(-qlen // (G * R))
-                if npass > 3 and qlen > 200:
+                if npass > 3 and qlen > 200 and geom == 1:
                     continue
                 db.set_shape(G, R, lane_mode)
                 best = 1e9
@@ -33,6 +35,6 @@ with Database(residues, offsets) as db:
                 if ref is None:
                     ref = s.copy()
                 ok = bool(np.array_equal(ref, s))
-                print(json.dumps({"qlen": qlen, "G": G, "R": R, "mode": lane_mode, "npass": npass,
+                print(json.dumps({"geom": geom, "qlen": qlen, "G": G, "R": R, "mode": lane_mode, "npass": npass,
                                   "scan_ms": round(best, 3), "gcups": round(cells / best * 1e-6, 1),
                                   "same": ok, "requeued": db.last_counters["gpu_requeued"]}), flush=True)
