@@ -63,6 +63,7 @@ struct ScanParams
   u32 negq;                   // both lanes: -(gap open + extend) in the mode's encoding
   u32 negr;                   // both lanes: -(gap extend), two's complement
   u32 padword;                // both lanes: score of a padding query row
+  int stagger;                // geometry 2: odd stages build the next block's tables after their tile
 };
 
 __device__ __forceinline__ u32 swb_hadd2(u32 a, u32 b)
@@ -315,13 +316,17 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   const u32 xout_toggle = xout0 ^ (xout0 + xhalf);
 
   // builds column g & 3 of stream k's table for block words (x, y) at byte offset slot_off
+  u32 bmask = 0;                                     // bit j: this thread builds row brow + j * RG
+#pragma unroll
+  for (int j = 0; j < NBJ; j++)
+    if (brow + j * RG < nq) bmask |= 1u << j;
   auto build = [&](const uint2 blkw, const u32 slot_off) {
     const u32 da = bsrc + ((blkw.x >> bshift) & 63u) * (2u * SWB_MS_STRIDE);
     const u32 db = bsrc + ((blkw.y >> bshift) & 63u) * (2u * SWB_MS_STRIDE);
     const u32 dst = bdst + slot_off;
 #pragma unroll
     for (int j = 0; j < NBJ; j++)
-      if (brow + j * RG < nq)
+      if (bmask & (1u << j))
         swb_sts32(dst + j * RG * 128, swb_pack16(swb_lds16(da + j * RG * 2), swb_lds16(db + j * RG * 2)));
     if (g == 0) swb_sts32(hdr + slot_off, (blkw.x >> 6) & 3u);
   };
@@ -344,6 +349,8 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
     const bool spill = MP && (pass + 1 < npass) && (g == G - 1);
 
     if (MP && pass > 0) __syncthreads();               // the previous pass is done with ring and mailboxes
+    uint4 pfh = make_uint4(0, 0, 0, 0), pff = make_uint4(0, 0, 0, 0);
+    if (MP && feed && nblk > 0) { pfh = P.bndH[bnd0]; pff = P.bndF[bnd0]; }
     uint2 nxt = make_uint2(0, 0);                      // block t + 1
     if (nblk > 0) build(swb_ldg_blk(blk), 0);
     if (nblk > 1) nxt = swb_ldg_blk(blk + 1);
@@ -373,11 +380,16 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
         if0 = vf.x; if1 = vf.y; if2 = vf.z; if3 = vf.w;
         is = swb_lds32(xin + 32);
       }
-      if (MP && feed && active)
+      if (MP && feed)
       {
-        const uint4 vh = P.bndH[bnd0 + b], vf = P.bndF[bnd0 + b];
-        ih0 = vh.x; ih1 = vh.y; ih2 = vh.z; ih3 = vh.w;
-        if0 = vf.x; if1 = vf.y; if2 = vf.z; if3 = vf.w;
+        // the previous pass's bottom row of this block was fetched one step ago; the fetch for the next
+        // block is issued now, a whole tile ahead of its use, so its latency never stalls the pipeline
+        if (active)
+        {
+          ih0 = pfh.x; ih1 = pfh.y; ih2 = pfh.z; ih3 = pfh.w;
+          if0 = pff.x; if1 = pff.y; if2 = pff.z; if3 = pff.w;
+        }
+        if (b + 1 < nblk) { pfh = P.bndH[bnd0 + b + 1]; pff = P.bndF[bnd0 + b + 1]; }
       }
       if (flags & SWB_FLAG_START)
       {
@@ -389,20 +401,36 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       smax = __vmaxs2(smax, is);
       u32 hup0 = ih0, hup1 = ih1, hup2 = ih2, hup3 = ih3;
       u32 f0 = if0, f1 = if1, f2 = if2, f3 = if3;
-      u32 dg = dtop;
+      // H[i] = H(row i, last column of the previous block) is the diagonal input of row i + 1; the first
+      // operation of that row's first cell is issued one row early (with its score load), so H[i]'s
+      // register is free again when row i's own last column is written back into it -- no register
+      // rotation at the loop's back edge.
+      uint4 sc = swb_lds128(rq[0] + roff);
+      u32 a0 = swb_cell_pre<MODE>(dtop, sc.x, E[0]);
       dtop = ih3;
 #pragma unroll
       for (int i = 0; i < R; i++)
       {
-        const uint4 sc = swb_lds128(rq[i] + roff);
-        u32 hd = dg, e = E[i], h;
-        dg = H[i];
-        swb_cell<MODE>(hd, sc.x, e, f0, h, smax, negq, negr); hd = hup0; hup0 = h;
-        swb_cell<MODE>(hd, sc.y, e, f1, h, smax, negq, negr); hd = hup1; hup1 = h;
-        swb_cell<MODE>(hd, sc.z, e, f2, h, smax, negq, negr); hd = hup2; hup2 = h;
-        swb_cell<MODE>(hd, sc.w, e, f3, h, smax, negq, negr); hup3 = h;
+        uint4 scn = sc;
+        u32 an = 0;
+        if (i + 1 < R)
+        {
+          scn = swb_lds128(rq[i + 1] + roff);
+          an = swb_cell_pre<MODE>(H[i], scn.x, E[i + 1]);
+        }
+        u32 e = E[i], h, a;
+        swb_cell_post<MODE>(a0, e, f0, h, smax, negq, negr);
+        a = swb_cell_pre<MODE>(hup0, sc.y, e); hup0 = h;
+        swb_cell_post<MODE>(a, e, f1, h, smax, negq, negr);
+        a = swb_cell_pre<MODE>(hup1, sc.z, e); hup1 = h;
+        swb_cell_post<MODE>(a, e, f2, h, smax, negq, negr);
+        a = swb_cell_pre<MODE>(hup2, sc.w, e); hup2 = h;
+        swb_cell_post<MODE>(a, e, f3, h, smax, negq, negr);
+        hup3 = h;
         H[i] = h;
         E[i] = e;
+        sc = scn;
+        a0 = an;
       }
       if (MP && spill && active)
       {
@@ -596,7 +624,11 @@ __global__ void __launch_bounds__(SWB2_STREAMS * G, 16 / G) swb_scan2_kernel(con
       const uint2 cur = nxt;
       if (t + 2 < nblk) nxt = swb_ldg_blk(pnext);
       pnext++;
-      build(cur, woff, t + 1 < nblk);
+      // Even stages build before their tile, odd stages after it: the barrier puts all G warps of the SM
+      // at the same point of the step, and this keeps half of them in the (ALU-free) build phase while
+      // the other half is in the DP tile.
+      const bool build_late = P.stagger && (g & 1);
+      if (!build_late) build(cur, woff, t + 1 < nblk);
       if (MP && feed)
       {
         if (t + 1 < nblk)                              // top row of block t + 1 -> the other parity
@@ -679,6 +711,7 @@ __global__ void __launch_bounds__(SWB2_STREAMS * G, 16 / G) swb_scan2_kernel(con
         swb_sts128(xout0 + wpar + 512u, make_uint4(f0, f1, f2, f3));
         swb_sts32(xs0 + 2u * SWB2_XFER + wpar, smax | flagbits);
       }
+      if (build_late) build(cur, woff, t + 1 < nblk);
       now = cur;
       woff = woff + slot_bytes == ring_bytes ? 0u : woff + slot_bytes;
       roff = roff + slot_bytes == ring_bytes ? 0u : roff + slot_bytes;

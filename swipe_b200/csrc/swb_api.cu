@@ -695,6 +695,8 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     P.bndH = db->bndH.p; P.bndF = db->bndF.p;
     P.nq = tb.nq; P.npass = npass;
     P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
+    P.stagger = 1;
+    if (const char *env = getenv("SWB_STAGGER")) P.stagger = atoi(env) != 0;
     SWB_CUDA(cudaEventRecord(db->ev[0], st));
     // While the shard is arriving, consecutive groups alternate between two streams: the CTAs of the
     // next launch fill the SMs as those of the previous one drain, so the launch boundary costs nothing.
@@ -822,6 +824,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       const unsigned r16 = (unsigned)(unsigned short)(short)(-sc->gap_extend);
       const unsigned p16 = (unsigned)(unsigned short)enc16(SWB_PAD_SCORE, SWB_MODE_INT16);
       P2.negq = q16 | (q16 << 16); P2.negr = r16 | (r16 << 16); P2.padword = p16 | (p16 << 16);
+      P2.stagger = P.stagger;
       fn16<<<grid16, threads16, smem16, st>>>(P2);
       SWB_CUDA(cudaGetLastError());
       const int limit16 = 32767 - (int)std::max<long long>(tb.hi, 0);
