@@ -73,19 +73,21 @@ def parse_args():
     ap.add_argument("--no-weak", action="store_true")
     ap.add_argument("--no-product-path", action="store_true")
     ap.add_argument("--shape", default="", help="G,R,lane_mode test hook")
+    ap.add_argument("--batch", type=int, default=1,
+                    help="distinct queries per step, searched with swb_search_hits_batch (protein configs, N=1)")
     return ap.parse_args()
 
 
 class Workload:
     """The synthetic inputs of one config: queries (one per strand), database, scoring."""
 
-    def __init__(self, cfg, nseq, qlen):
+    def __init__(self, cfg, nseq, qlen, batch=1):
         from swipe_b200 import scoring, synth
         self.kind = cfg["kind"]
         self.gap_open, self.gap_extend = cfg["gap_open"], cfg["gap_extend"]
         if self.kind == "protein":
             q = synth.protein_query(qlen) if qlen == 375 else synth.protein_query(qlen, seed=20261017 + qlen)
-            self.queries = [q]
+            self.queries = [q] + [synth.protein_query(qlen, seed=20261017 + qlen + 31 * k) for k in range(1, batch)]
             # planted homologs always derive from the 375-aa query so every config scans the same database
             self.residues, self.offsets = synth.protein_db(nseq, query=synth.protein_query(375))
             self.matrix = scoring.blosum62()
@@ -374,8 +376,12 @@ def main():
         if avail < nseq * 200 * 3.2:                    # codes + pinned copy + generator scratch
             nseq = int(avail // (200 * 3.2))
         set_cache_limit(64 << 30)                       # the e2e loop re-opens a 10 GB shard every step
-    w = Workload(cfg, nseq, qlen)
+    w = Workload(cfg, nseq, qlen, args.batch if cfg["kind"] == "protein" and world == 1 else 1)
     config = base_config(args, cfg, w.nseq, qlen, world)
+    batched = len(w.queries) > 1 and cfg["kind"] == "protein"
+    if batched:
+        config["batch"] = "%d distinct %d-aa queries per step through swb_search_hits_batch (one shared scan where they fit)" % (
+            len(w.queries), qlen)
     sc = Scoring(w.matrix, w.gap_open, w.gap_extend)
     nq = len(w.queries)
 
@@ -410,7 +416,17 @@ def main():
         the per-rank hit lists and the merge on rank 0.  Returns rank 0's merged (seqnos, scores)."""
         t0 = time.perf_counter()
         lists = []
-        for s, q in enumerate(w.queries):
+        if batched:
+            res = db.search_hits_batch(w.queries, sc, TOPK, 1, 2 ** 62, seqno_base=lo)
+            for s, (seq, scv, tot, obv) in enumerate(res):
+                lists.append((seq * nq + s, scv))
+            if record is not None:
+                for c in db.last_batch_counters:
+                    record["launches"] += c["kernel_launches"]
+                    record["scan_ms"].append(c["scan_ms"])
+                    record["requeue_ms"].append(c["requeue_ms"])
+                    record["counters"] = c
+        for s, q in enumerate(w.queries if not batched else []):
             seq, scv, tot, obv = db.search_hits(q, sc, TOPK, 1, 2 ** 62, seqno_base=lo)
             lists.append((seq * nq + s, scv))            # strand in the low bit keeps (seqno, strand) unique
             if record is not None:

@@ -208,6 +208,20 @@ int swb_search_hits(swb_db *db, const uint8_t *query, int64_t qlen, const swb_sc
                     int64_t *out_seqno, int64_t *out_score, int64_t *nhits, int64_t *totalhits,
                     int64_t *obvious, swb_counters *counters);
 
+/* swb_search_batch / swb_search_hits_batch: several queries against the shard, the reference's query
+ * loop (swipe.cc:2561) folded into as few scans as possible.  Queries that fit side by side on the 16
+ * pipeline stages of the scan kernel (sum of ceil(qlen / 25) <= 16, i.e. up to 400 query rows) share ONE
+ * pass over the residue stream and ONE substitution-table build per 4-column block; longer ones are
+ * searched one after the other.  Results are exactly those of nqueries separate swb_search /
+ * swb_search_hits calls (tests/test_gpu_batch.py): scores[k][i] / the hit list of query k.  counters,
+ * when given, is an array of nqueries entries; the shared scan's time is split evenly over its queries. */
+int swb_search_batch(swb_db *db, int nqueries, const uint8_t *const *queries, const int64_t *qlens,
+                     const swb_scoring *scoring, int64_t *const *scores, swb_counters *counters);
+int swb_search_hits_batch(swb_db *db, int nqueries, const uint8_t *const *queries, const int64_t *qlens,
+                          const swb_scoring *scoring, int64_t seqno_base, int64_t keep, int64_t min_score,
+                          int64_t upper_score, int64_t *const *out_seqno, int64_t *const *out_score,
+                          int64_t *nhits, int64_t *totalhits, int64_t *obvious, swb_counters *counters);
+
 /* Merges hit lists that are each in the sink's order (what swb_search_hits returns) into the best
  * `keep` overall -- the master's merge of the reference's MPI build (swipe.cc:1957-1974) and the
  * host-side step of a multi-GPU search.  Returns the number of hits written or a negative status. */

@@ -21,7 +21,7 @@ EXPORTS = ["swb_abi_version", "swb_align", "swb_alu_peak", "swb_blastdb_close", 
            "swb_host_alloc", "swb_host_free", "swb_last_cuda_error", "swb_matrix_builtin",
            "swb_matrix_limits", "swb_matrix_nucleotide", "swb_matrix_parse", "swb_matrix_read",
            "swb_matrix_read_sound", "swb_query_parse", "swb_revcomp", "swb_search",
-           "swb_search_end", "swb_search_hits", "swb_search_list", "swb_set_cache_limit",
+           "swb_search_batch", "swb_search_end", "swb_search_hits", "swb_search_hits_batch", "swb_search_list", "swb_set_cache_limit",
            "swb_hits_merge", "swb_set_geometry", "swb_set_mode", "swb_set_shape",
            "swb_stats_bits", "swb_stats_default_gaps", "swb_stats_evalue", "swb_stats_init",
            "swb_stats_length_adjustment", "swb_stats_params", "swb_stats_params_nt", "swb_strerror",
@@ -88,6 +88,13 @@ def load_library():
     lib.swb_search_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Scoring), C.c_int64,
                                     C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, p64, p64,
                                     p64, C.POINTER(Counters)]
+    lib.swb_search_batch.restype = C.c_int
+    lib.swb_search_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), p64, C.POINTER(_Scoring),
+                                     C.POINTER(C.c_void_p), C.POINTER(Counters)]
+    lib.swb_search_hits_batch.restype = C.c_int
+    lib.swb_search_hits_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), p64, C.POINTER(_Scoring),
+                                          C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p), p64, p64, p64, C.POINTER(Counters)]
     lib.swb_hits_merge.restype = C.c_int64
     lib.swb_hits_merge.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), p64, C.c_int64,
                                    C.c_void_p, C.c_void_p]
@@ -354,6 +361,41 @@ class Database:
                                          C.byref(k), C.byref(tot), C.byref(obv), C.byref(ctr)))
         self.last_counters = ctr.as_dict()
         return self._hit_seq[:k.value].copy(), self._hit_sc[:k.value].copy(), tot.value, obv.value
+
+    def search_batch(self, queries, scoring):
+        """swb_search_batch: list of score arrays, one per query (queries sharing scans where they fit)."""
+        qs = [_u8(q) for q in queries]
+        n = len(qs)
+        out = [np.empty(self.nseq, dtype=np.int64) for _ in qs]
+        qp = (C.c_void_p * max(n, 1))(*[q.ctypes.data for q in qs])
+        ql = (C.c_int64 * max(n, 1))(*[q.size for q in qs])
+        op = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in out])
+        ctr = (Counters * max(n, 1))()
+        sc = scoring._c()
+        _check(self._lib.swb_search_batch(self._h, n, qp, ql, C.byref(sc), op, ctr))
+        self.last_batch_counters = [ctr[k].as_dict() for k in range(n)]
+        return out
+
+    def search_hits_batch(self, queries, scoring, keep, min_score=1, upper_score=2 ** 62, seqno_base=0):
+        """swb_search_hits_batch: [(seqnos, scores, totalhits, obvious)] per query."""
+        qs = [_u8(q) for q in queries]
+        n = len(qs)
+        keep = int(keep)
+        seqs = [np.empty(max(keep, 1), dtype=np.int64) for _ in qs]
+        scs = [np.empty(max(keep, 1), dtype=np.int64) for _ in qs]
+        qp = (C.c_void_p * max(n, 1))(*[q.ctypes.data for q in qs])
+        ql = (C.c_int64 * max(n, 1))(*[q.size for q in qs])
+        p1 = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in seqs])
+        p2 = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in scs])
+        nh = (C.c_int64 * max(n, 1))()
+        tot = (C.c_int64 * max(n, 1))()
+        obv = (C.c_int64 * max(n, 1))()
+        ctr = (Counters * max(n, 1))()
+        sc = scoring._c()
+        _check(self._lib.swb_search_hits_batch(self._h, n, qp, ql, C.byref(sc), int(seqno_base), keep,
+                                               int(min_score), int(upper_score), p1, p2, nh, tot, obv, ctr))
+        self.last_batch_counters = [ctr[k].as_dict() for k in range(n)]
+        return [(seqs[k][:nh[k]].copy(), scs[k][:nh[k]].copy(), tot[k], obv[k]) for k in range(n)]
 
     def search_list(self, query, scoring, seqnos):
         """seqnos: plain sequence numbers; coded (seqno << 3) for the ABI as the reference does."""

@@ -45,8 +45,9 @@ struct ScanSeg
   const uint2 *blocks;        // [total_blocks] 8 residues each: bytes 0-3 lane A cols 0-3, 4-7 lane B
   const long long *pairblk;   // [npairs+1] exclusive prefix of blocks per pair
   const int *stream_pair;     // [nstreams+1] first pair of every stream
-  u32 *pair_scores;           // [npairs] packed lane maxima
+  u32 *pair_scores;           // [npairs] packed lane maxima (a batch: [queries][score_stride])
   long long bnd_base;         // first entry of this chunk in bndH / bndF
+  long long score_stride;     // batched queries: distance between two queries' pair_scores
 };
 
 struct ScanParams
@@ -64,6 +65,12 @@ struct ScanParams
   u32 negr;                   // both lanes: -(gap extend), two's complement
   u32 padword;                // both lanes: score of a padding query row
   int stagger;                // geometry 2: odd stages build the next block's tables after their tile
+  // Batched queries (geometry 2, single pass): several queries lie one after the other in the pipeline,
+  // each on whole stages.  Bit g of start_mask: stage g holds the first rows of a query (its input is
+  // zeros, not the previous stage's bottom row); bit g of end_mask: stage g holds a query's last rows and
+  // stores its scores; stage_query[g]: which query that is.  A single query: 1, 1 << (G - 1), zeros.
+  u32 start_mask, end_mask;
+  unsigned char stage_query[32];
 };
 
 __device__ __forceinline__ u32 swb_hadd2(u32 a, u32 b)
@@ -554,6 +561,8 @@ __global__ void __launch_bounds__(SWB2_STREAMS * G, 16 / G) swb_scan2_kernel(con
   const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);   // every warp holds all 32 streams
   const int nsteps = nblk_max > 0 ? nblk_max + G - 1 : 0;
   const u32 negq = (KQ | KR) ? KQ : P.negq, negr = (KQ | KR) ? KR : P.negr;
+  const bool qstart = (P.start_mask >> g) & 1u, qend = (P.end_mask >> g) & 1u;
+  u32 *qscores = S.pair_scores + (long long)P.stage_query[g] * S.score_stride;
   // table build: this thread fills ONE column of its stream's table, rows brow, brow + RG, ...; the
   // column rotates with the lane's octet so that the 32 STS.32 of a warp fall into 32 different banks
   const int bcol = ((lane >> 3) + g) & 3;
@@ -641,10 +650,12 @@ __global__ void __launch_bounds__(SWB2_STREAMS * G, 16 / G) swb_scan2_kernel(con
 
       // ---- stage g works on block b = t - g ----------------------------------------------------------
       const bool active = b >= 0 && b < nblk;
-      const uint4 vh = swb_lds128(xin0 + par), vf = swb_lds128(xin0 + par + 512u);
+      uint4 vh = make_uint4(0, 0, 0, 0), vf = make_uint4(0, 0, 0, 0);
       u32 is;
+      if (g == 0 || !qstart) { vh = swb_lds128(xin0 + par); vf = swb_lds128(xin0 + par + 512u); }
       if (g == 0) is = ((now.x >> 6) & 1u) * SWB2_FLAG_START + ((now.x >> 7) & 1u) * SWB2_FLAG_END;
       else is = swb_lds32(xs0 + par);
+      if (qstart) is &= SWB2_FLAG_START | SWB2_FLAG_END;     // a query's first stage inherits no maximum
       if (is & SWB2_FLAG_START)
       {
 #pragma unroll
@@ -687,7 +698,7 @@ __global__ void __launch_bounds__(SWB2_STREAMS * G, 16 / G) swb_scan2_kernel(con
         sc = scn;
         a0 = an;
       }
-      if (g == G - 1)
+      if (qend)
       {
         if (MP && spill && active)
         {
@@ -697,12 +708,12 @@ __global__ void __launch_bounds__(SWB2_STREAMS * G, 16 / G) swb_scan2_kernel(con
         if (active && (flagbits & SWB2_FLAG_END))
         {
           u32 v = smax;
-          if (MP && pass > 0) v = __vmaxs2(v, S.pair_scores[pair_out]);
-          S.pair_scores[pair_out] = v;
+          if (MP && pass > 0) v = __vmaxs2(v, qscores[pair_out]);
+          qscores[pair_out] = v;
           pair_out++;
         }
       }
-      else
+      if (g < G - 1)
       {
         // ---- hand the strip's bottom row to the next stage ------------------------------------------
         // (written to the parity the next stage reads at step t + 1; it is reading the other one now)

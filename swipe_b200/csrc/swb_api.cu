@@ -187,6 +187,13 @@ struct Layout
 
 struct Shape { int G, R; };
 
+// A batched scan (swb_search_batch) has already run the first tier for this query: the packed lane
+// maxima of chunk k are at pair_scores[k] and search_impl starts from there.
+struct Prescan
+{
+  std::vector<const u32 *> pair_scores;
+};
+
 // swb_search_hits: the sink's admission rule applied on the device (see swb_hist_kernel)
 struct HitsReq
 {
@@ -240,6 +247,7 @@ struct swb_db
   std::vector<unsigned long long> h_cand;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_group[2] = {nullptr, nullptr};   // completion of the last two scan launches
+  cudaEvent_t ev_batch[2] = {nullptr, nullptr};   // around a batched scan launch
   double upload_ms = 0, layout_ms = 0;
   int force_G = 0, force_R = 0, force_mode = -1;   // test hooks (swb_set_shape)
   int force_geom = 0;                              // 0 = automatic, 1 / 2 = scan kernel geometry (swb_set_geometry)
@@ -398,7 +406,7 @@ const ShapeEntry g_shapes[] = {
     SWB_SHAPE(16, 20), SWB_SHAPE(16, 24), SWB_SHAPE(32, 12), SWB_SHAPE(32, 16), SWB_SHAPE(32, 20),
     SWB_SHAPE(32, 24), SWB_SHAPE(32, 28), SWB_SHAPE(32, 32),
     // geometry 2 (one warp = one stage of 32 streams)
-    SWB_SHAPE2(16, 20), SWB_SHAPE2(16, 21), SWB_SHAPE2(16, 24), SWB_SHAPE2(4, 25),
+    SWB_SHAPE2(16, 20), SWB_SHAPE2(16, 21), SWB_SHAPE2(16, 24), SWB_SHAPE2(16, 25), SWB_SHAPE2(4, 25),
 };
 const int g_nshapes = (int)(sizeof(g_shapes) / sizeof(g_shapes[0]));
 
@@ -408,10 +416,14 @@ const int g_nshapes = (int)(sizeof(g_shapes) / sizeof(g_shapes[0]));
 // single pass / multi-pass.  Shapes without a multi-pass measurement use 0.93 x single pass.
 struct ShapeEff { int geom, G, R; double sp, mp; };
 const ShapeEff g_eff[] = {
-    {1, 8, 8, 5.0, 0},     {1, 8, 13, 5.52, 0},    {1, 8, 16, 6.00, 0},    {1, 16, 12, 6.42, 0},   {1, 16, 16, 7.04, 0},
-    {1, 16, 20, 7.09, 0},  {1, 16, 24, 7.19, 6.18}, {1, 32, 12, 6.36, 5.71}, {1, 32, 16, 6.64, 6.44}, {1, 32, 20, 6.80, 6.74},
-    {1, 32, 24, 7.50, 6.45}, {1, 32, 28, 7.39, 6.41}, {1, 32, 32, 6.62, 6.38},
-    {2, 16, 20, 7.0, 6.8}, {2, 16, 21, 7.0, 6.8}, {2, 16, 24, 7.2, 6.9}, {2, 4, 25, 5.5, 5.0},
+    // geometry 1: r1 table scaled by what the round-2 row loop / boundary prefetch measured (x 1.025 single
+    // pass, x 1.037 multi-pass), with the shapes re-measured in round 2 entered as measured
+    // (profiles/r2_tune_shapes.txt)
+    {1, 8, 8, 5.12, 0},     {1, 8, 13, 5.70, 0},    {1, 8, 16, 6.15, 0},    {1, 16, 12, 6.58, 0},   {1, 16, 16, 7.22, 0},
+    {1, 16, 20, 7.27, 0},  {1, 16, 24, 7.61, 6.41}, {1, 32, 12, 6.52, 5.92}, {1, 32, 16, 6.81, 6.68}, {1, 32, 20, 6.97, 6.99},
+    {1, 32, 24, 7.69, 6.69}, {1, 32, 28, 7.57, 6.65}, {1, 32, 32, 6.36, 6.62},
+    // geometry 2 (measured): only ahead for short queries, where its four-stage CTA amortises the table build
+    {2, 16, 20, 6.5, 5.9}, {2, 16, 21, 6.6, 6.08}, {2, 16, 24, 6.92, 5.3}, {2, 16, 25, 6.9, 5.3}, {2, 4, 25, 5.82, 5.0},
 };
 
 // (kq, kr): the penalties in the mode's packed encoding; a build with exactly these compiled in is
@@ -430,7 +442,7 @@ const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, u32 k
   const ShapeEntry *best = nullptr;
   double best_rate = 0;
   const bool allow_spec = getenv("SWB_NO_SPEC") == nullptr;
-  int geom = db->force_geom;
+  int geom = db->force_geom;                   // 0: both geometries compete on measured efficiency
   if (geom == 0)
     if (const char *env = getenv("SWB_GEOM")) geom = atoi(env);
   for (int i = 0; i < g_nshapes; i++)
@@ -448,7 +460,6 @@ const ShapeEntry *choose_shape(const swb_db *db, long long qlen, int mode, u32 k
     for (const ShapeEff &e : g_eff)
       if (e.G == s.G && e.R == s.R && e.geom == s.geom) eff = np > 1 ? (e.mp > 0 ? e.mp : 0.93 * e.sp) : e.sp;
     if (!spec) eff *= 0.955;                                   // generic builds read the penalties from registers
-    else if (s.geom == 1 && s.G == 32 && s.R == 32 && np == 1) eff *= 0.87;   // this one spills with the immediates (5.60 vs 6.13)
     if (mode == SWB_MODE_INT16) eff *= 0.84;
     const double rate = eff * (double)std::max<long long>(qlen, 1) / (double)(np * rows);
     if (!best || rate > best_rate) { best = &s; best_rate = rate; *npass = (int)np; }
@@ -512,7 +523,7 @@ int check_args(const swb_db *db, const unsigned char *query, long long qlen, con
 // The cascade over n subjects (the whole shard when h_list == NULL).
 int search_impl(swb_db *db, const unsigned char *query, long long qlen, const swb_scoring *sc,
                 const long long *h_list, long long n, long long *scores, long long *bestpos,
-                long long *bestq, swb_counters *ctr, HitsReq *hits = nullptr)
+                long long *bestq, swb_counters *ctr, HitsReq *hits = nullptr, const Prescan *pre = nullptr)
 {
   SWB_TRY(check_args(db, query, qlen, sc));
   if (n < 0 || (n > 0 && !scores && !hits)) return SWB_ERR_ARG;
@@ -611,6 +622,28 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     }
     else
       layouts = db->chunks;
+    const int limit = (mode != SWB_MODE_INT16 ? 2047 : 32767) - (int)std::max<long long>(tb.hi, 0);
+    int stagger = 1;
+    if (const char *env = getenv("SWB_STAGGER")) stagger = atoi(env) != 0;
+    SWB_TRY(db->requeue.reserve((size_t)n));
+    if (pre)
+    {
+      // first tier done by a batched launch: unpack its lane maxima, queue what left the exact range
+      SWB_CUDA(cudaEventRecord(db->ev[0], st));
+      size_t k = 0;
+      for (Layout *L : layouts)
+      {
+        if (L->n == 0) continue;
+        if (k >= pre->pair_scores.size()) return SWB_ERR_INTERNAL;
+        swb_finish_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(
+            pre->pair_scores[k++], L->idx_out.p, L->n, L->first, limit, nullptr, db->scores.p, db->requeue.p,
+            db->counters.p);
+        SWB_CUDA(cudaGetLastError());
+        launches++;
+      }
+    }
+    else
+    {
     // launch geometry: one CTA = 8 streams x G stages; as many CTAs per SM as shared memory
     // and registers allow
     const int threads = shape_threads(*shape);
@@ -679,7 +712,6 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       SWB_TRY(db->bndH.reserve((size_t)sum_blocks));
       SWB_TRY(db->bndF.reserve((size_t)sum_blocks));
     }
-    SWB_TRY(db->requeue.reserve((size_t)n));
     SWB_TRY(db->segs.reserve(std::max<size_t>(segs.size(), 1)));
     if (!segs.empty())
       SWB_CUDA(cudaMemcpyAsync(db->segs.p, segs.data(), segs.size() * sizeof(ScanSeg),
@@ -688,15 +720,14 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     const unsigned nq16 = (unsigned)(unsigned short)enc16(-q, mode);
     const unsigned nr16 = (unsigned)(unsigned short)(short)(-r);
     const unsigned pad16 = (unsigned)(unsigned short)enc16(SWB_PAD_SCORE, mode);
-    const int limit = (mode != SWB_MODE_INT16 ? 2047 : 32767) - (int)std::max<long long>(tb.hi, 0);
     ScanParams P;
     memset(&P, 0, sizeof P);
     P.m16 = db->m16.p; P.qrow_off = db->qrow_off.p;
     P.bndH = db->bndH.p; P.bndF = db->bndF.p;
     P.nq = tb.nq; P.npass = npass;
     P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
-    P.stagger = 1;
-    if (const char *env = getenv("SWB_STAGGER")) P.stagger = atoi(env) != 0;
+    P.stagger = stagger;
+    P.start_mask = 1u; P.end_mask = 1u << (shape->G - 1);
     SWB_CUDA(cudaEventRecord(db->ev[0], st));
     // While the shard is arriving, consecutive groups alternate between two streams: the CTAs of the
     // next launch fill the SMs as those of the previous one drain, so the launch boundary costs nothing.
@@ -756,6 +787,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     }
     if (two_streams && group_no >= 2)
       SWB_CUDA(cudaStreamWaitEvent(st, db->ev_group[1], 0));     // the last launch on stream2 (odd groups)
+    }
     SWB_CUDA(cudaEventRecord(db->ev[1], st));
     unsigned long long h_nreq = 0;
     SWB_CUDA(cudaMemcpyAsync(&h_nreq, db->counters.p, sizeof h_nreq, cudaMemcpyDeviceToHost, st));
@@ -824,7 +856,8 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       const unsigned r16 = (unsigned)(unsigned short)(short)(-sc->gap_extend);
       const unsigned p16 = (unsigned)(unsigned short)enc16(SWB_PAD_SCORE, SWB_MODE_INT16);
       P2.negq = q16 | (q16 << 16); P2.negr = r16 | (r16 << 16); P2.padword = p16 | (p16 << 16);
-      P2.stagger = P.stagger;
+      P2.stagger = stagger;
+      P2.start_mask = 1u; P2.end_mask = 1u << (sh16->G - 1);
       fn16<<<grid16, threads16, smem16, st>>>(P2);
       SWB_CUDA(cudaGetLastError());
       const int limit16 = 32767 - (int)std::max<long long>(tb.hi, 0);
@@ -974,10 +1007,226 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
   return SWB_OK;
 }
 
+// ---- several queries per scan (the reference loops over its queries one search at a
+// time, swipe.cc:2561) --------------------------------------------------------------------------------
+// Queries are laid one after the other along the pipeline of the geometry-2 kernel, each on whole stages
+// (ScanParams::start_mask / end_mask): one pass over the residue stream and ONE table build per block
+// serve all of them, which is what a short query cannot amortise on its own.  The first tier runs
+// batched; unpacking, the re-queue tiers and the sink then run per query through search_impl (Prescan).
+const ShapeEntry *find_shape(int geom, int G, int R, int mode, u32 kq, u32 kr)
+{
+  const ShapeEntry *generic = nullptr;
+  const bool allow_spec = getenv("SWB_NO_SPEC") == nullptr;
+  for (int i = 0; i < g_nshapes; i++)
+  {
+    const ShapeEntry &s = g_shapes[i];
+    if (s.geom != geom || s.G != G || s.R != R || s.mode != mode) continue;
+    if ((s.kq | s.kr) == 0) generic = &s;
+    else if (allow_spec && s.kq == kq && s.kr == kr) return &s;
+  }
+  return generic;
+}
+
+int batch_impl(swb_db *db, int nqueries, const uint8_t *const *queries, const int64_t *qlens,
+               const swb_scoring *sc, int64_t *const *scores, HitsReq *hits, swb_counters *counters)
+{
+  if (!db || nqueries < 0 || (nqueries > 0 && (!queries || !qlens))) return SWB_ERR_ARG;
+  if (!hits && nqueries > 0 && !scores) return SWB_ERR_ARG;
+  for (int k = 0; k < nqueries; k++)
+    SWB_TRY(check_args(db, queries[k], qlens[k], sc));
+  SWB_CUDA(cudaSetDevice(db->device));
+  SWB_TRY(swb_db_wait(db));
+  cudaStream_t st = db->stream;
+  auto single = [&](int k, const Prescan *pre) {
+    return search_impl(db, queries[k], qlens[k], sc, nullptr, db->nseq, scores ? (long long *)scores[k] : nullptr,
+                       nullptr, nullptr, counters ? counters + k : nullptr, hits ? hits + k : nullptr, pre);
+  };
+  // can the packed kernels hold this scoring system at all, and in which lane arithmetic?
+  int mode = SWB_MODE_HYBRID;
+  if (db->force_mode >= 0) mode = db->force_mode;
+  bool packed = db->mode == 0 && db->nseq > 0 && db->force_geom != 1 && getenv("SWB_NO_BATCH") == nullptr;
+  u32 kq = 0, kr = 0;
+  if (packed)
+  {
+    Tables probe;
+    const unsigned char none = 0;
+    SWB_TRY(prepare_tables(probe, &none, 0, sc, mode, 0));
+    if (mode != SWB_MODE_INT16 && !probe.hybrid_ok) mode = SWB_MODE_INT16;
+    packed = probe.narrow_ok;
+    if (mode == SWB_MODE_HYBRID && sc->gap_open_extend <= 1023 && sc->gap_extend >= 1 && sc->gap_extend <= 1023)
+    {
+      const u32 a = (u32)(unsigned short)enc16(-sc->gap_open_extend, mode), b = (u32)(unsigned short)(short)(-sc->gap_extend);
+      kq = a | (a << 16);
+      kr = b | (b << 16);
+    }
+  }
+  const int G = 16;
+  const int cand_R[] = {25, 24, 21, 20};
+  int k0 = 0;
+  while (k0 < nqueries)
+  {
+    // the next group: as many of the following queries as fit the 16 stages, with the rows-per-stage
+    // that wastes the fewest pipeline rows
+    int best_m = 1, best_R = 0;
+    double best_fill = 0;
+    for (int R : cand_R)
+    {
+      if (!packed || !find_shape(2, G, R, mode, kq, kr)) continue;
+      int stages = 0, m = 0;
+      long long rows = 0;
+      for (int k = k0; k < nqueries; k++)
+      {
+        const long long need = (qlens[k] + R - 1) / R;
+        if (qlens[k] <= 0 || stages + need > G) break;
+        stages += (int)need;
+        rows += qlens[k];
+        m++;
+      }
+      const double fill = (double)rows / (double)(G * R);
+      if (m >= 2 && fill > best_fill) { best_fill = fill; best_m = m; best_R = R; }
+    }
+    if (best_m < 2)
+    {
+      SWB_TRY(single(k0, nullptr));
+      k0++;
+      continue;
+    }
+    const int m = best_m, R = best_R;
+    const ShapeEntry *shape = find_shape(2, G, R, mode, kq, kr);
+    // tables over the union of the group's symbols; query rows in pipeline order, padded per query
+    std::vector<unsigned char> cat;
+    for (int k = k0; k < k0 + m; k++) cat.insert(cat.end(), queries[k], queries[k] + qlens[k]);
+    Tables tb;
+    SWB_TRY(prepare_tables(tb, cat.data(), (long long)cat.size(), sc, mode, 0, 0));
+    const size_t smem = shape_smem(*shape, tb.nq);
+    if (smem + 1024 > SWB_SMEM_LIMIT)
+    {
+      SWB_TRY(single(k0, nullptr));              // too many distinct symbols for the one-CTA ring
+      k0++;
+      continue;
+    }
+    ScanParams P;
+    memset(&P, 0, sizeof P);
+    std::vector<unsigned short> qrow((size_t)G * R, (unsigned short)(tb.nq * 16));
+    int stage = 0;
+    for (int k = k0; k < k0 + m; k++)
+    {
+      const int need = (int)((qlens[k] + R - 1) / R);
+      P.start_mask |= 1u << stage;
+      P.end_mask |= 1u << (stage + need - 1);
+      for (int g = stage; g < stage + need; g++) P.stage_query[g] = (unsigned char)(k - k0);
+      for (long long i = 0; i < qlens[k]; i++)
+        qrow[(size_t)stage * R + (size_t)i] = (unsigned short)(tb.rowof[queries[k][i]] * 16);
+      stage += need;
+    }
+    if (stage < G) P.start_mask |= 1u << stage;    // idle tail stages: cut off from the last query
+    const int threads = shape_threads(*shape);
+    const scan_fn fn = shape->fn;
+    SWB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, threads, smem));
+    if (occ < 1) return SWB_ERR_INTERNAL;
+    const int grid = db->sm_count * occ;
+    const int nstreams = grid * shape_streams(*shape);
+    std::vector<Layout *> work;
+    for (Layout *L : db->chunks)
+      if (L->n > 0) work.push_back(L);
+    if (work.size() > 65535) return SWB_ERR_RANGE;
+    std::vector<ScanSeg> segs(work.size());
+    for (size_t c = 0; c < work.size(); c++)
+    {
+      Layout *L = work[c];
+      if (L->stream_pair_n != nstreams)
+      {
+        SWB_TRY(L->stream_pair.reserve((size_t)nstreams + 1));
+        swb_partition_kernel<<<(nstreams + 1 + 255) / 256, 256, 0, st>>>(L->pairblk.p, L->npairs, nstreams,
+                                                                         L->stream_pair.p);
+        SWB_CUDA(cudaGetLastError());
+        L->stream_pair_n = nstreams;
+      }
+      SWB_TRY(L->pair_scores.reserve((size_t)L->npairs * (size_t)m));
+      SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * (size_t)m * sizeof(u32), st));
+      ScanSeg &S = segs[c];
+      S.blocks = L->blocks.p; S.pairblk = L->pairblk.p; S.stream_pair = L->stream_pair.p;
+      S.pair_scores = L->pair_scores.p; S.bnd_base = 0; S.score_stride = L->npairs;
+    }
+    SWB_TRY(db->m16.reserve(SWB_M16_BYTES / sizeof(short)));
+    SWB_TRY(db->qrow_off.reserve(qrow.size()));
+    SWB_TRY(db->segs.reserve(std::max<size_t>(segs.size(), 1)));
+    SWB_CUDA(cudaMemcpyAsync(db->m16.p, tb.m16.data(), tb.m16.size() * sizeof(short), cudaMemcpyHostToDevice, st));
+    SWB_CUDA(cudaMemcpyAsync(db->qrow_off.p, qrow.data(), qrow.size() * sizeof(unsigned short),
+                             cudaMemcpyHostToDevice, st));
+    SWB_CUDA(cudaMemcpyAsync(db->segs.p, segs.data(), segs.size() * sizeof(ScanSeg), cudaMemcpyHostToDevice, st));
+    const unsigned nq16 = (unsigned)(unsigned short)enc16(-sc->gap_open_extend, mode);
+    const unsigned nr16 = (unsigned)(unsigned short)(short)(-sc->gap_extend);
+    const unsigned pad16 = (unsigned)(unsigned short)enc16(SWB_PAD_SCORE, mode);
+    P.m16 = db->m16.p; P.qrow_off = db->qrow_off.p;
+    P.nq = tb.nq; P.npass = 1;
+    P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
+    P.stagger = 1;
+    if (const char *env = getenv("SWB_STAGGER")) P.stagger = atoi(env) != 0;
+    P.seg = segs[0];
+    P.segs = db->segs.p;
+    SWB_CUDA(cudaEventRecord(db->ev_batch[0], st));
+    fn<<<dim3((unsigned)grid, (unsigned)work.size()), threads, smem, st>>>(P);
+    SWB_CUDA(cudaGetLastError());
+    SWB_CUDA(cudaEventRecord(db->ev_batch[1], st));
+    for (int k = k0; k < k0 + m; k++)
+    {
+      Prescan pre;
+      for (Layout *L : work) pre.pair_scores.push_back(L->pair_scores.p + (size_t)(k - k0) * (size_t)L->npairs);
+      SWB_TRY(single(k, &pre));
+    }
+    float ms = 0;
+    SWB_CUDA(cudaEventElapsedTime(&ms, db->ev_batch[0], db->ev_batch[1]));
+    if (counters)
+      for (int k = k0; k < k0 + m; k++)
+      {
+        counters[k].scan_ms += ms / m;             // the shared scan, split evenly over the group
+        counters[k].kernel_launches += k == k0 ? 1 : 0;
+      }
+    k0 += m;
+  }
+  return SWB_OK;
+}
+
 }  // namespace
 
 // ============================================================================================
 extern "C" {
+
+int swb_search_batch(swb_db *db, int nqueries, const uint8_t *const *queries, const int64_t *qlens,
+                     const swb_scoring *scoring, int64_t *const *scores, swb_counters *counters)
+{
+  if (nqueries > 0 && !scores) return SWB_ERR_ARG;
+  return batch_impl(db, nqueries, queries, qlens, scoring, scores, nullptr, counters);
+}
+
+int swb_search_hits_batch(swb_db *db, int nqueries, const uint8_t *const *queries, const int64_t *qlens,
+                          const swb_scoring *scoring, int64_t seqno_base, int64_t keep, int64_t min_score,
+                          int64_t upper_score, int64_t *const *out_seqno, int64_t *const *out_score,
+                          int64_t *nhits, int64_t *totalhits, int64_t *obvious, swb_counters *counters)
+{
+  if (nqueries < 0 || keep < 0 || (nqueries > 0 && (!nhits || (keep > 0 && (!out_seqno || !out_score)))))
+    return SWB_ERR_ARG;
+  std::vector<HitsReq> H((size_t)std::max(nqueries, 0));
+  for (int k = 0; k < nqueries; k++)
+  {
+    H[(size_t)k].seqno_base = seqno_base; H[(size_t)k].keep = keep;
+    H[(size_t)k].min_score = min_score; H[(size_t)k].upper = upper_score;
+    H[(size_t)k].out_seqno = keep > 0 ? (long long *)out_seqno[k] : nullptr;
+    H[(size_t)k].out_score = keep > 0 ? (long long *)out_score[k] : nullptr;
+  }
+  const int rc = batch_impl(db, nqueries, queries, qlens, scoring, nullptr, H.data(), counters);
+  if (rc != SWB_OK) return rc;
+  for (int k = 0; k < nqueries; k++)
+  {
+    nhits[k] = H[(size_t)k].nhits;
+    if (totalhits) totalhits[k] = H[(size_t)k].totalhits;
+    if (obvious) obvious[k] = H[(size_t)k].obvious;
+  }
+  return SWB_OK;
+}
 
 int swb_abi_version(void) { return SWB_ABI_VERSION; }
 
@@ -1213,6 +1462,7 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
     for (int i = 0; i < 4; i++) SWB_CUDA(cudaEventCreate(&db->ev[i]));
     for (int i = 0; i < 2; i++) SWB_CUDA(cudaEventCreateWithFlags(&db->ev_group[i], cudaEventDisableTiming));
     for (int i = 0; i < 3; i++) SWB_CUDA(cudaEventCreate(&db->ev_open[i]));
+    for (int i = 0; i < 2; i++) SWB_CUDA(cudaEventCreate(&db->ev_batch[i]));
     SWB_CUDA(cudaEventCreateWithFlags(&db->ev_uploaded, cudaEventDisableTiming));
     SWB_TRY(db->residues.reserve((size_t)offsets[nseq] + 16));
     SWB_TRY(db->offsets.reserve((size_t)nseq + 1));
@@ -1549,6 +1799,8 @@ int swb_db_close(swb_db *db)
     if (db->ev_open[i]) cudaEventDestroy(db->ev_open[i]);
   for (int i = 0; i < 2; i++)
     if (db->ev_group[i]) cudaEventDestroy(db->ev_group[i]);
+  for (int i = 0; i < 2; i++)
+    if (db->ev_batch[i]) cudaEventDestroy(db->ev_batch[i]);
   if (db->ev_uploaded) cudaEventDestroy(db->ev_uploaded);
   if (db->copy_stream) cudaStreamDestroy(db->copy_stream);
   if (db->layout_stream) cudaStreamDestroy(db->layout_stream);
