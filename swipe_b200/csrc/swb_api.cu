@@ -688,6 +688,11 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     for (Layout *L : work)
       if (L->ev_ready && cudaEventQuery(L->ev_ready) != cudaSuccess) resident = false;
     (void)cudaGetLastError();
+    if (!resident && getenv("SWB_WAIT_RESIDENT") != nullptr)      // tuning hook: no overlap of upload and scan
+    {
+      SWB_TRY(swb_db_wait(db));
+      resident = true;
+    }
     if (merge && resident && !getenv("SWB_OVERSUB")) oversub = work.size() >= 4 ? 1 : oversub;
     const int grid = db->sm_count * occ * oversub;
     const int nstreams = grid * cta_streams;

@@ -341,9 +341,31 @@ void search_shard(Run &R, const Query &q, Shard &S)
     for (int qframe = 0; qframe <= qf2; qframe++)
     {
       const std::vector<uint8_t> &qv = query_variant(R, q, qstrand, qframe);
+      const bool filtered = R.memb_bit != 0 || !R.taxids.empty();
+      if (!filtered && unit == 1 && R.keephits > 0)
+      {
+        // every subject takes part and subject = sequence: the sink runs on the device
+        // (swb_search_hits) and only the hits hits_enter would have kept come back
+        std::vector<int64_t> hs((size_t)R.keephits), hv((size_t)R.keephits);
+        int64_t nh = 0, t = 0, ob = 0;
+        check(swb_search_hits(S.db, qv.data(), (int64_t)qv.size(), &sc, S.first, R.keephits, R.st.score_threshold,
+                              R.st.upper_threshold, hs.data(), hv.data(), &nh, &t, &ob, nullptr), "search");
+        computed += nsub;
+        tot += t;
+        obv += ob;
+        for (int64_t k = 0; k < nh; k++)
+        {
+          Hit h;
+          h.seqno = hs[(size_t)k];
+          h.score = hv[(size_t)k];
+          if (o.symtype == 0 && qstrand) { h.qstrand = 0; h.dstrand = 1; }     // swipe.cc:1470-1471
+          else { h.qstrand = qstrand; h.qframe = qframe; h.dstrand = 0; h.dframe = 0; }
+          local.push_back(h);
+        }
+        continue;
+      }
       check(swb_search(S.db, qv.data(), (int64_t)qv.size(), &sc, scores.data(), nullptr), "search");
       int64_t threshold = R.st.score_threshold;
-      const bool filtered = R.memb_bit != 0 || !R.taxids.empty();
       if (!filtered) computed += nsub;
       for (int64_t j = 0; j < nsub; j++)
       {
