@@ -43,8 +43,19 @@ def build_lib(force=False, verbose=False):
         if os.path.exists(LIB):
             return LIB
         raise RuntimeError("nvcc not found and %s is not built" % LIB)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    subprocess.run(cmd, cwd=CSRC, check=True)
+    # several ranks of one job may get here at once: one builds (under a file lock, into a temporary
+    # file that is renamed when complete), the others wait and find the library fresh
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale(LIB, DEPS):
+                tmp = LIB + ".tmp.%d" % os.getpid()
+                cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+                subprocess.run(cmd, cwd=CSRC, check=True)
+                os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
