@@ -104,17 +104,6 @@ class Workload:
         self.cells = float(self.total_res) * self.qlen * len(self.queries)
 
 
-def shard_cuts(offsets, world):
-    """Sequence ranges [lo, hi) per rank holding equal shares of the residues (the cut swipe-b200 -a N
-    makes, swipe_main.cpp)."""
-    total = int(offsets[-1])
-    cuts = [0]
-    for r in range(1, world):
-        cuts.append(int(np.searchsorted(offsets, total * r // world, side="left")))
-    cuts.append(int(offsets.size - 1))
-    return [(max(cuts[r], cuts[r - 1] if r else 0), max(cuts[r + 1], cuts[r])) for r in range(world)]
-
-
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons while the timed region runs (NVML, else nvidia-smi)."""
 
@@ -362,6 +351,7 @@ def main():
     import torch
     import torch.distributed as dist
     from swipe_b200 import (Database, Scoring, HostBuffer, topk_merge, hits_merge, set_cache_limit, alu_peak)
+    from swipe_b200.shard import shard_cuts, HitExchange
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the scan has no CPU path")
@@ -399,17 +389,14 @@ def main():
 
     stream = torch.cuda.Stream()
     shape = [int(x) for x in args.shape.split(",")] if args.shape else None
-    gather_buf = torch.empty((TOPK * nq, 2), dtype=torch.int64).pin_memory()
-    gather_dev = torch.empty((TOPK * nq, 2), dtype=torch.int64, device="cuda")
-    gathered_dev = [torch.empty_like(gather_dev) for _ in range(world)] if world > 1 else None
-    gathered_host = torch.empty((world, TOPK * nq, 2), dtype=torch.int64).pin_memory() if world > 1 else None
+    exchange = HitExchange(TOPK, nq, device=torch.device("cuda", local_rank) if world > 1 else None, stream=stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    split = {"search": 0.0, "gather": 0.0, "merge": 0.0}
+    split = {"search": 0.0, "gather_and_merge": 0.0}
 
     def step(db, record=None):
         """One pass of the hot path over this rank's shard: scan(s) + device sink, then the exchange of
@@ -436,38 +423,11 @@ def main():
                 record["requeue_ms"].append(c["requeue_ms"])
                 record["counters"] = c
         t1 = time.perf_counter()
-        merged = None
-        if world > 1:
-            with torch.cuda.stream(stream):
-                gather_buf.fill_(-1)
-                at = 0
-                for seq, scv in lists:
-                    gather_buf[at: at + seq.size, 0] = torch.from_numpy(seq)
-                    gather_buf[at: at + seq.size, 1] = torch.from_numpy(scv)
-                    at += TOPK
-                gather_dev.copy_(gather_buf, non_blocking=True)
-                dist.all_gather(gathered_dev, gather_dev)
-                if rank == 0:
-                    for r in range(world):
-                        gathered_host[r].copy_(gathered_dev[r], non_blocking=True)
-            stream.synchronize()
-            t2 = time.perf_counter()
-            if rank == 0:
-                g = gathered_host.numpy()
-                parts = []
-                for r in range(world):
-                    for s in range(nq):
-                        blk = g[r, s * TOPK: (s + 1) * TOPK]
-                        k = int((blk[:, 0] >= 0).sum())
-                        parts.append((blk[:k, 0], blk[:k, 1]))
-                merged = hits_merge(parts, TOPK)
-        else:
-            t2 = t1
-            merged = hits_merge(lists, TOPK) if nq > 1 else lists[0]
+        t2 = t1
+        merged = exchange(lists)                         # all_gather of K pairs per rank + swb_hits_merge on rank 0
         t3 = time.perf_counter()
         split["search"] += t1 - t0
-        split["gather"] += t2 - t1
-        split["merge"] += t3 - t2
+        split["gather_and_merge"] += t3 - t2
         return merged
 
     # ---- the 1-GPU answer the sharded run must reproduce (rank 0, outside the timed region) ----------
@@ -524,6 +484,18 @@ def main():
         else:
             ref_list = hits_merge(local_lists, TOPK)
             topk_identical = bool(np.array_equal(merged[0], ref_list[0]) and np.array_equal(merged[1], ref_list[1]))
+    # the alignment phase's device part (search16s's contract, swipe.cc:381-393): exact score + end cell
+    # of the K best hits of the first query, as align_chunk asks for them
+    end_cell = None
+    if rank == 0 and local_lists and len(local_lists[0][0]):
+        top = (local_lists[0][0] // nq) - lo
+        db.search_end(w.queries[0], sc, top)             # warm-up (scratch allocation)
+        t0 = time.perf_counter()
+        es, ep, eq = db.search_end(w.queries[0], sc, top)
+        end_cell = {"what": "swb_search_end over the %d best hits of this shard (search16s: score, first column "
+                            "reaching it, smallest row in it)" % top.size,
+                    "subjects": int(top.size), "ms": (time.perf_counter() - t0) * 1e3,
+                    "scores_equal_scan": bool(np.array_equal(es, local_lists[0][1]))}
     dense_first_strand = None
     if world == 1 and not args.no_cpu_baseline:
         db.search(w.queries[0], sc, out=dense)
@@ -696,8 +668,8 @@ def main():
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                                  "note": "not the binding bound (SURVEY 8d): 1 byte per residue per scan"}},
             "split_ms": {"scan_kernel_max_over_ranks": scan_max * nq, "search_call_max_over_ranks": search_max,
-                         "sink_and_d2h": max(0.0, search_max - scan_max * nq), "gather": res_split["gather"],
-                         "merge": res_split["merge"], "step": ms_all / args.steps},
+                         "sink_and_d2h": max(0.0, search_max - scan_max * nq),
+                         "gather_and_merge": res_split["gather_and_merge"], "step": ms_all / args.steps},
             "counters": {k: rec["counters"][k] for k in ("ref_width7", "ref_width16", "ref_width63", "gpu_narrow",
                                                          "gpu_requeued", "gpu_middle", "kernel_launches")},
             "requeue_ms": float(np.mean(rec["requeue_ms"])),
@@ -706,7 +678,7 @@ def main():
         }
         sp = line["split_ms"]
         parts = {"scan": sp["scan_kernel_max_over_ranks"], "sink_and_d2h": sp["sink_and_d2h"],
-                 "gather": sp["gather"], "merge": sp["merge"]}
+                 "gather_and_merge": sp["gather_and_merge"]}
         line["split_ms"]["limiter"] = max(parts, key=parts.get)
         if e2e_all:
             line["e2e"] = {"value": w.cells * args.steps / (e2e_all * 1e-3) * 1e-9, "unit": "GCUPS",
@@ -716,6 +688,8 @@ def main():
             line["weak"] = {"value": w.cells * world * weak_steps / (weak_all * 1e-3) * 1e-9, "unit": "GCUPS",
                             "ms_per_step": weak_all / weak_steps, "steps": weak_steps,
                             "what": "every GPU scans its own full copy of the database (per-GPU work fixed)"}
+        if end_cell:
+            line["alignment_phase"] = end_cell
         if product:
             line["product_path"] = product
         if world == 1 and not args.no_cpu_baseline:

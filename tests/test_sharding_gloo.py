@@ -35,6 +35,19 @@ def _worker(rank, world, port, out_dir):
     seq, sc, _, _ = shard.local_topk(scores, lo, keep=40, min_score=20)
     gseq, gsc = shard.gather_topk(seq, sc, 40)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), seq=gseq, sc=gsc)
+    # the bench's N > 1 path: ONE database cut by residue count, per-rank hit lists (two "strands" here),
+    # gathered and merged on rank 0 with swb_hits_merge
+    a, b = shard.shard_cuts(offsets, world)[rank]
+    sc2, _, _ = Oracle().scan(residues[offsets[a]:offsets[b]], offsets[a:b + 1] - offsets[a], q, m, 11, 1, threads=1)
+    lists = []
+    for strand in range(2):
+        s_, v_, _, _ = shard.local_topk(sc2 + strand, a, keep=25, min_score=20)
+        lists.append((s_ * 2 + strand, v_))
+    merged = shard.HitExchange(25, 2)(lists)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "exchange.npz"), seq=merged[0], sc=merged[1], cut=np.array([a, b]))
+    else:
+        assert merged is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,3 +63,12 @@ def test_two_rank_topk_merge(tmp_path, oracle):
     for r in range(2):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
         assert np.array_equal(got["seq"], want_seq) and np.array_equal(got["sc"], want_sc)
+    # HitExchange over residue-balanced shards and two lists per rank = the sink over everything
+    ex = np.load(os.path.join(str(tmp_path), "exchange.npz"))
+    allseq = np.concatenate([np.arange(501) * 2, np.arange(501) * 2 + 1])
+    allsc = np.concatenate([scores, scores + 1])
+    want2_seq, want2_sc, _, _ = oracle.topk(allseq, allsc, 25, min_score=20)
+    # (strand 1 was filtered at min_score 20 AFTER the +1, like strand 0: same rule on both)
+    assert np.array_equal(ex["seq"], want2_seq) and np.array_equal(ex["sc"], want2_sc)
+    half = int(offsets[-1]) // 2
+    assert abs(int(offsets[ex["cut"][1]]) - half) <= int((offsets[1:] - offsets[:-1]).max())
