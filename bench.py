@@ -653,7 +653,10 @@ def main():
             "gpu_launches": launches_all,
             "roofline": {"bound": "int-alu-issue", "achieved": kernel_gcups, "peak": peak_gcups, "unit": "GCUPS",
                          "frac": kernel_gcups / peak_gcups,
-                         "kernel": "swb_scan_kernel", "kernel_ms": scan_avg,
+                         "kernel": "%s<G=%d,R=%d,hybrid fp16-pattern/DPX lanes>, %d pass(es)" % (
+                             "swb_scan2_kernel" if rec["counters"]["scan_geometry"] == 2 else "swb_scan_kernel",
+                             rec["counters"]["scan_G"], rec["counters"]["scan_R"], rec["counters"]["scan_passes"]),
+                         "kernel_ms": scan_avg,
                          "cells_per_launch": my_cells_per_scan, "cells_per_clk_per_sm": cells_clk_sm,
                          "peak_cells_per_clk_per_sm": peak_cells_clk_sm,
                          "dpx_warp_instr_per_clk_per_sm_measured": dpx_rate, "dpx_per_cell_pair": dpx_per_cell_pair,

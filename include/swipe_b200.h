@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SWB_ABI_VERSION 1
+#define SWB_ABI_VERSION 2
 #define SWB_MATRIX_DIM 32 /* reference swipe.h:66-68: score tables are 32 x 32 */
 
 typedef enum swb_status
@@ -81,6 +81,10 @@ typedef struct swb_counters
   int64_t kernel_launches;/* CUDA kernels launched by this call                                */
   double scan_ms;         /* device time of the scan kernels (CUDA events on the handle stream)*/
   double requeue_ms;      /* device time of the wide re-queue kernels                          */
+  /* which build of the scan kernel ran the first tier (0 when it was skipped): geometry 1 = a warp
+     holds four pipeline stages of eight streams, 2 = a warp is one stage of 32 streams; G stages of
+     R query rows each, `scan_passes` passes over the residue stream (ABI version 2)                */
+  int64_t scan_geometry, scan_G, scan_R, scan_passes;
 } swb_counters;
 
 typedef struct swb_db swb_db; /* opaque: one database shard resident on one GPU */

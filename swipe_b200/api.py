@@ -46,7 +46,8 @@ class Counters(C.Structure):
     _fields_ = [("subjects", C.c_int64), ("cells", C.c_int64), ("ref_width7", C.c_int64),
                 ("ref_width16", C.c_int64), ("ref_width63", C.c_int64), ("gpu_narrow", C.c_int64),
                 ("gpu_requeued", C.c_int64), ("gpu_middle", C.c_int64), ("kernel_launches", C.c_int64),
-                ("scan_ms", C.c_double), ("requeue_ms", C.c_double)]
+                ("scan_ms", C.c_double), ("requeue_ms", C.c_double), ("scan_geometry", C.c_int64),
+                ("scan_G", C.c_int64), ("scan_R", C.c_int64), ("scan_passes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -1003,6 +1003,10 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       hits->nhits = k; hits->totalhits = tot; hits->obvious = obv;
     }
   }
+  if (narrow && !pre)
+  {
+    c.scan_geometry = shape->geom; c.scan_G = shape->G; c.scan_R = shape->R; c.scan_passes = npass;
+  }
   c.gpu_requeued = nrequeue;
   c.gpu_narrow = n - nrequeue;
   c.kernel_launches = launches;
@@ -1188,6 +1192,7 @@ int batch_impl(swb_db *db, int nqueries, const uint8_t *const *queries, const in
       for (int k = k0; k < k0 + m; k++)
       {
         counters[k].scan_ms += ms / m;             // the shared scan, split evenly over the group
+        counters[k].scan_geometry = 2; counters[k].scan_G = G; counters[k].scan_R = R; counters[k].scan_passes = 1;
         counters[k].kernel_launches += k == k0 ? 1 : 0;
       }
     k0 += m;

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(api.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.swb_abi_version() == 1
+    assert lib.swb_abi_version() == 2
     assert lib.swb_strerror(0) == b"ok"
     assert b"no CPU path" in lib.swb_strerror(-2)
 
