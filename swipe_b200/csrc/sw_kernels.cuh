@@ -809,6 +809,91 @@ __global__ void __launch_bounds__(128) swb_wide_kernel(const WideParams P)
   if (END) { P.bestpos[item] = bd; P.bestq[item] = bq; }
 }
 
+// ---- end-cell kernel: one WARP per subject -----------------------------------------------------------
+// search16s's contract (search16s.cc:390-405, called for the hits that get an alignment, swipe.cc:381-393):
+// exact score, the first subject column in which it is reached and the smallest query row reaching it in
+// that column.  The 32 lanes of a warp own consecutive strips of S query rows (H and E of the strip in
+// registers) and sweep the subject as a wavefront: at step t lane l works on column t - l and hands the
+// bottom H / F of its strip to lane l + 1 by shuffle.  Every lane remembers its own first best cell; the
+// lanes' candidates are then reduced by (value, then column, then row).  32-bit cells; queries of up to
+// 32 S rows (S <= 32).  Longer queries and 64-bit scoring systems stay on swb_wide_kernel.
+template <int S>
+__global__ void __launch_bounds__(128) swb_end_kernel(const WideParams P)
+{
+  __shared__ int Msh[32 * 32];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) Msh[i] = (int)P.matrix[i];
+  __syncthreads();
+  const long long item0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (item0 >= P.nsel) return;                       // whole warps leave together
+  const int lane = threadIdx.x & 31;
+  const long long item = P.sel ? P.sel[item0] : item0;
+  const long long subj = P.list ? (P.list[item] >> 3) : item;
+  const bool rc = P.list ? ((P.list[item] >> 2) & 1) != 0 : false;
+  const long long o0 = P.offsets[subj];
+  const int dlen = (int)(P.offsets[subj + 1] - o0 - P.trailing);
+  const unsigned char *d = P.residues + o0;
+  const int qlen = P.qlen;
+  const int q = (int)P.q, r = (int)P.r;
+  const int row0 = lane * S;
+  int qsym[S], H[S], E[S];
+#pragma unroll
+  for (int i = 0; i < S; i++)
+  {
+    qsym[i] = row0 + i < qlen ? (int)P.query[row0 + i] : 0;
+    H[i] = 0;
+    E[i] = 0;
+  }
+  int best = 0, bcol = -1, brow = -1;
+  int hup_prev = 0;                                  // H of the row above the strip, previous column
+  int hbot = 0, fbot = 0;                            // bottom of this strip, the column just done
+  for (int t = 0; t < dlen + 31; t++)
+  {
+    // the strip above finished column t - lane one step ago
+    int hup = __shfl_up_sync(0xffffffffu, hbot, 1);
+    int fup = __shfl_up_sync(0xffffffffu, fbot, 1);
+    if (lane == 0) { hup = 0; fup = 0; }
+    const int j = t - lane;
+    if (j >= 0 && j < dlen)
+    {
+      unsigned sym = d[rc ? dlen - 1 - j : j] & 31;
+      if (rc) sym = ((sym & 1) << 3) | ((sym & 2) << 1) | ((sym & 4) >> 1) | ((sym & 8) >> 3);
+      const int *mrow = Msh + (sym << 5);
+      int diag = hup_prev, f = fup;
+#pragma unroll
+      for (int i = 0; i < S; i++)
+      {
+        int h = diag + mrow[qsym[i]];
+        h = max(max(h, E[i]), max(f, 0));
+        if (h > best && row0 + i < qlen) { best = h; bcol = j; brow = row0 + i; }
+        const int hq = h - q;
+        E[i] = max(E[i] - r, hq);
+        f = max(f - r, hq);
+        diag = H[i];
+        H[i] = h;
+      }
+      hbot = H[S - 1];
+      fbot = f;
+      hup_prev = hup;
+    }
+  }
+  // the warp's best cell: highest value, then first column, then smallest row
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+  {
+    const int ob = __shfl_down_sync(0xffffffffu, best, off);
+    const int oc = __shfl_down_sync(0xffffffffu, bcol, off);
+    const int orow = __shfl_down_sync(0xffffffffu, brow, off);
+    const bool better = ob > best || (ob == best && ob > 0 && (oc < bcol || (oc == bcol && orow < brow)));
+    if (better) { best = ob; bcol = oc; brow = orow; }
+  }
+  if (lane == 0)
+  {
+    P.scores[item] = best;
+    P.bestpos[item] = bcol;
+    P.bestq[item] = brow;
+  }
+}
+
 // ---- nucleotide ingest ---------------------------------------------------------------------------
 // One warp per subject: unpack the .nsq record (4 bases per byte, most significant pair first; the
 // last byte carries the remaining len % 4 bases) to the 4-bit one-hot codes A=1 C=2 G=4 T=8 and

@@ -473,6 +473,24 @@ int run_wide(swb_db *db, const long long *d_list, const long long *d_sel, long l
 {
   if (nsel == 0) return SWB_OK;
   cudaStream_t st = db->stream;
+  if (end && !use64 && qlen <= 1024 && getenv("SWB_NO_END_KERNEL") == nullptr)
+  {
+    // the alignment phase's few subjects: one warp each (swb_end_kernel), state in registers
+    WideParams W;
+    memset(&W, 0, sizeof W);
+    W.residues = db->residues.p; W.offsets = db->offsets.p; W.trailing = db->trailing;
+    W.list = d_list; W.sel = d_sel; W.nsel = nsel;
+    W.query = d_query; W.qlen = (int)qlen; W.matrix = db->matrix.p;
+    W.q = sc->gap_open_extend; W.r = sc->gap_extend;
+    W.scores = db->scores.p; W.bestpos = db->bestpos.p; W.bestq = db->bestq.p;
+    const unsigned grid = (unsigned)((nsel * 32 + 127) / 128);
+    if (qlen <= 256) swb_end_kernel<8><<<grid, 128, 0, st>>>(W);
+    else if (qlen <= 512) swb_end_kernel<16><<<grid, 128, 0, st>>>(W);
+    else swb_end_kernel<32><<<grid, 128, 0, st>>>(W);
+    SWB_CUDA(cudaGetLastError());
+    (*launches)++;
+    return SWB_OK;
+  }
   const long long batch = 1 << 16;
   const size_t cell = use64 ? 8 : 4;
   SWB_TRY(db->he.reserve((size_t)(2 * std::max<long long>(qlen, 1)) *

@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, call G: the whole GPU suite + every config as a bench line (both arms) + launch list + ncu per shape
+# (ncu reports are exported to CSV on the box and deleted: gpurun_out/ may carry 64 MiB back)
 mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/r2g_pytest_gpu.log 2>&1
 echo "pytest rc=$?"; tail -4 gpurun_out/r2g_pytest_gpu.log
@@ -15,13 +16,16 @@ timeout 1500 python bench.py --config nt50m --steps 3 --warmup 3 > gpurun_out/r2
 timeout 900 python bench.py --impl reference --config nt50m --steps 3 --warmup 1 > gpurun_out/r2g_bench_reference_nt50m.json 2>> gpurun_out/r2g_bench_nt50m.err; echo "nt ref rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2g_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2g_bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:swb_scan -s 1 -c 1 -f -o gpurun_out/r2g_prof_scan_375 \
-  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2g_ncu_375.log 2>&1
-for c in qlen100 qlen1000; do
-ncu --set full --clock-control none --import-source on -k regex:swb_scan -s 1 -c 1 -f -o gpurun_out/r2g_prof_scan_$c \
-  python bench.py --config $c --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --nseq 2000000 > gpurun_out/r2g_ncu_$c.log 2>&1
-done
-ncu --set full --clock-control none --import-source on -k regex:swb_scan -s 1 -c 1 -f -o gpurun_out/r2g_prof_scan_nt \
-  python bench.py --config nt50m --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --nseq 5000000 > gpurun_out/r2g_ncu_nt.log 2>&1
-ls -la gpurun_out/*.ncu-rep
-for f in gpurun_out/r2g_bench*.json; do echo "== $f"; tail -c 1200 $f; echo; done
+cap() {   # name, bench args...
+  local name=$1; shift
+  ncu --set full --clock-control none --import-source on -k regex:swb_scan -s 1 -c 1 -f -o /tmp/prof_$name \
+    python bench.py "$@" --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2g_ncu_$name.log 2>&1
+  ncu -i /tmp/prof_$name.ncu-rep --page raw --csv > gpurun_out/r2g_ncu_${name}_raw.csv 2>/dev/null
+  ncu -i /tmp/prof_$name.ncu-rep --page source --csv > gpurun_out/r2g_ncu_${name}_source.csv 2>/dev/null
+  rm -f /tmp/prof_$name.ncu-rep
+}
+cap 375
+cap qlen100 --config qlen100 --nseq 2000000
+cap qlen1000 --config qlen1000 --nseq 2000000
+cap nt --config nt50m --nseq 5000000
+du -sh gpurun_out
