@@ -365,7 +365,9 @@ def main():
         avail = psutil.virtual_memory().available
         if avail < nseq * 200 * 3.2:                    # codes + pinned copy + generator scratch
             nseq = int(avail // (200 * 3.2))
-        set_cache_limit(64 << 30)                       # the e2e loop re-opens a 10 GB shard every step
+    # the e2e loop re-opens the shard every step: let the library keep its device buffers (shard, layout,
+    # pass-boundary scratch) between handles instead of returning gigabytes to the driver at every close
+    set_cache_limit(96 << 30)
     w = Workload(cfg, nseq, qlen, args.batch if cfg["kind"] == "protein" and world == 1 else 1)
     config = base_config(args, cfg, w.nseq, qlen, world)
     batched = len(w.queries) > 1 and cfg["kind"] == "protein"
