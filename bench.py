@@ -359,6 +359,7 @@ def main():
     if world > 1:
         bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")       # host-side waits that must not occupy the GPUs
 
     if cfg["kind"] == "nt":
         import psutil
@@ -561,6 +562,8 @@ def main():
     product = None
     if world > 1:
         barrier()
+        # (the other ranks wait on the gloo group below: an NCCL barrier would spin a kernel on their GPUs,
+        # which rank 0 is about to use from its own context)
         if rank == 0 and not args.no_product_path and torch.cuda.device_count() >= world:
             cuts = shard_cuts(w.offsets, world)
             dbs = []
@@ -597,6 +600,7 @@ def main():
                        "timing": "host wall clock around N threads (each search ends in a stream synchronize)",
                        "topk_identical": bool(np.array_equal(pm[0], single[0]) and np.array_equal(pm[1], single[1])),
                        "what": "one process, one host thread + swb_db handle per GPU, swb_search_hits + swb_hits_merge"}
+        dist.barrier(group=cpu_group)
         barrier()
 
     # ---- reduce over ranks --------------------------------------------------------------------------------

@@ -815,8 +815,8 @@ __global__ void __launch_bounds__(128) swb_wide_kernel(const WideParams P)
 // that column.  The 32 lanes of a warp own consecutive strips of S query rows (H and E of the strip in
 // registers) and sweep the subject as a wavefront: at step t lane l works on column t - l and hands the
 // bottom H / F of its strip to lane l + 1 by shuffle.  Every lane remembers its own first best cell; the
-// lanes' candidates are then reduced by (value, then column, then row).  32-bit cells; queries of up to
-// 32 S rows (S <= 32).  Longer queries and 64-bit scoring systems stay on swb_wide_kernel.
+// lanes' candidates are then reduced by (value, then column, then row).  32-bit cells; 64-bit scoring
+// systems stay on swb_wide_kernel.
 template <int S>
 __global__ void __launch_bounds__(128) swb_end_kernel(const WideParams P)
 {
@@ -834,46 +834,62 @@ __global__ void __launch_bounds__(128) swb_end_kernel(const WideParams P)
   const unsigned char *d = P.residues + o0;
   const int qlen = P.qlen;
   const int q = (int)P.q, r = (int)P.r;
-  const int row0 = lane * S;
-  int qsym[S], H[S], E[S];
-#pragma unroll
-  for (int i = 0; i < S; i++)
-  {
-    qsym[i] = row0 + i < qlen ? (int)P.query[row0 + i] : 0;
-    H[i] = 0;
-    E[i] = 0;
-  }
+  // queries of more than 32 S rows: passes of 32 S rows; the bottom row of a pass (H and F per subject
+  // column) waits in global scratch for lane 0 of the next pass.  Lane 31 writes column j 31 steps after
+  // lane 0 has read it, so one pair of arrays serves every pass.
+  const int npass = (qlen + 32 * S - 1) / (32 * S);
+  int *bndH = (int *)P.he + item0 * 2 * P.stride, *bndF = bndH + P.stride;
   int best = 0, bcol = -1, brow = -1;
-  int hup_prev = 0;                                  // H of the row above the strip, previous column
-  int hbot = 0, fbot = 0;                            // bottom of this strip, the column just done
-  for (int t = 0; t < dlen + 31; t++)
+  for (int pass = 0; pass < npass; pass++)
   {
-    // the strip above finished column t - lane one step ago
-    int hup = __shfl_up_sync(0xffffffffu, hbot, 1);
-    int fup = __shfl_up_sync(0xffffffffu, fbot, 1);
-    if (lane == 0) { hup = 0; fup = 0; }
-    const int j = t - lane;
-    if (j >= 0 && j < dlen)
-    {
-      unsigned sym = d[rc ? dlen - 1 - j : j] & 31;
-      if (rc) sym = ((sym & 1) << 3) | ((sym & 2) << 1) | ((sym & 4) >> 1) | ((sym & 8) >> 3);
-      const int *mrow = Msh + (sym << 5);
-      int diag = hup_prev, f = fup;
+    const int row0 = (pass * 32 + lane) * S;
+    int qsym[S], H[S], E[S];
 #pragma unroll
-      for (int i = 0; i < S; i++)
+    for (int i = 0; i < S; i++)
+    {
+      qsym[i] = row0 + i < qlen ? (int)P.query[row0 + i] : 0;
+      H[i] = 0;
+      E[i] = 0;
+    }
+    int hup_prev = 0;                                // H of the row above the strip, previous column
+    int hbot = 0, fbot = 0;                          // bottom of this strip, the column just done
+    __syncwarp();
+    for (int t = 0; t < dlen + 31; t++)
+    {
+      // the strip above finished column t - lane one step ago
+      int hup = __shfl_up_sync(0xffffffffu, hbot, 1);
+      int fup = __shfl_up_sync(0xffffffffu, fbot, 1);
+      const int j = t - lane;
+      if (lane == 0)
       {
-        int h = diag + mrow[qsym[i]];
-        h = max(max(h, E[i]), max(f, 0));
-        if (h > best && row0 + i < qlen) { best = h; bcol = j; brow = row0 + i; }
-        const int hq = h - q;
-        E[i] = max(E[i] - r, hq);
-        f = max(f - r, hq);
-        diag = H[i];
-        H[i] = h;
+        hup = 0; fup = 0;
+        if (pass > 0 && j < dlen) { hup = bndH[j]; fup = bndF[j]; }
       }
-      hbot = H[S - 1];
-      fbot = f;
-      hup_prev = hup;
+      if (j >= 0 && j < dlen)
+      {
+        unsigned sym = d[rc ? dlen - 1 - j : j] & 31;
+        if (rc) sym = ((sym & 1) << 3) | ((sym & 2) << 1) | ((sym & 4) >> 1) | ((sym & 8) >> 3);
+        const int *mrow = Msh + (sym << 5);
+        int diag = hup_prev, f = fup;
+#pragma unroll
+        for (int i = 0; i < S; i++)
+        {
+          int h = diag + mrow[qsym[i]];
+          h = max(max(h, E[i]), max(f, 0));
+          // first column reaching the maximum, smallest row in it: later passes hold larger rows, so on
+          // equal values only a smaller column takes over
+          if ((h > best || (h == best && h > 0 && j < bcol)) && row0 + i < qlen) { best = h; bcol = j; brow = row0 + i; }
+          const int hq = h - q;
+          E[i] = max(E[i] - r, hq);
+          f = max(f - r, hq);
+          diag = H[i];
+          H[i] = h;
+        }
+        hbot = H[S - 1];
+        fbot = f;
+        hup_prev = hup;
+        if (lane == 31 && pass + 1 < npass) { bndH[j] = hbot; bndF[j] = fbot; }
+      }
     }
   }
   // the warp's best cell: highest value, then first column, then smallest row

@@ -473,11 +473,18 @@ int run_wide(swb_db *db, const long long *d_list, const long long *d_sel, long l
 {
   if (nsel == 0) return SWB_OK;
   cudaStream_t st = db->stream;
-  if (end && !use64 && qlen <= 1024 && getenv("SWB_NO_END_KERNEL") == nullptr)
+  if (end && !use64 && getenv("SWB_NO_END_KERNEL") == nullptr)
   {
-    // the alignment phase's few subjects: one warp each (swb_end_kernel), state in registers
+    // the alignment phase's few subjects: one warp each (swb_end_kernel), state in registers; queries
+    // beyond 1024 rows go in passes with the pass boundary (2 ints per subject column) in scratch
     WideParams W;
     memset(&W, 0, sizeof W);
+    if (qlen > 1024)
+    {
+      SWB_TRY(db->he.reserve((size_t)nsel * 2 * (size_t)std::max<long long>(db->longest, 1) * sizeof(int)));
+      W.he = db->he.p;
+      W.stride = std::max<long long>(db->longest, 1);
+    }
     W.residues = db->residues.p; W.offsets = db->offsets.p; W.trailing = db->trailing;
     W.list = d_list; W.sel = d_sel; W.nsel = nsel;
     W.query = d_query; W.qlen = (int)qlen; W.matrix = db->matrix.p;

@@ -441,3 +441,33 @@ def test_nucleotide_one_million_reads_vs_reference():
             bad = np.nonzero(got != exp)[0]
             assert bad.size == 0, "%s strand: %d scores differ, first %s" % (name, bad.size, bad[:5])
             assert got.max() > 100                      # the planted copies are found
+
+
+@pytest.mark.parametrize("qlen", [1, 40, 256, 257, 600, 1024, 1025, 2500])
+def test_end_cells_every_query_length(oracle, qlen):
+    """swb_search_end (search16s's contract, search16s.cc:390-405) through the warp-per-subject kernel:
+    every strip width (8 / 16 / 32 rows per lane), queries beyond 1024 rows in passes, and subjects that
+    repeat a piece of the query so that the maximum is reached in several cells (the first column, then the
+    smallest row, must be reported)."""
+    rng = np.random.default_rng(qlen)
+    q = synth.protein_query(qlen, seed=700 + qlen)
+    subs = []
+    for i in range(60):
+        L = int(rng.integers(1, 1500))
+        s = synth.random_protein(rng, L)
+        if i % 3 == 0 and qlen >= 8:
+            w = int(rng.integers(4, min(qlen, 200) + 1))
+            a = int(rng.integers(0, qlen - w + 1))
+            piece = q[a:a + w]
+            s = np.concatenate([s[:L // 3], piece, s[L // 3: L // 2], piece, s[L // 2:]])    # the same best score twice
+        subs.append(s)
+    subs.append(q.copy())
+    subs.append(np.concatenate([q, q]))
+    residues, offsets = fixtures.pack(subs)
+    sc = Scoring(B62, 11, 1)
+    sel = np.arange(len(subs))
+    with Database(residues, offsets) as db:
+        s, bp, bq = db.search_end(q, sc, sel)
+    for k in sel:
+        es, ed, eq = oracle.score_end(residues[offsets[k]:offsets[k + 1]], q, B62, 11, 1)
+        assert (s[k], bp[k], bq[k]) == (es, ed, eq), "subject %d (len %d)" % (k, offsets[k + 1] - offsets[k])
