@@ -46,7 +46,6 @@ struct ScanSeg
   const long long *pairblk;   // [npairs+1] exclusive prefix of blocks per pair
   const int *stream_pair;     // [nstreams+1] first pair of every stream
   u32 *pair_scores;           // [npairs] packed lane maxima (a batch: [queries][score_stride])
-  long long bnd_base;         // first entry of this chunk in bndH / bndF
   long long score_stride;     // batched queries: distance between two queries' pair_scores
 };
 
@@ -57,8 +56,15 @@ struct ScanParams
   const short *m16;           // [33][34] (SWB_M16_BYTES) score of (subject code, table row) in the mode's
                               // encoding, laid out as it is staged in shared memory
   const unsigned short *qrow_off; // [npass*G*R] 16 * (table row of every query row)
-  uint4 *bndH;                // [total_blocks] bottom H of a pass (only when npass > 1)
+  // Multi-pass scans: the bottom row of a pass waits here for the next pass.  A CTA only needs the rows of
+  // its own streams while it runs, so the scratch is sized for the RESIDENT CTAs, not for the shard: a CTA
+  // claims one of `nslots` regions of bnd_cta entries (bnd_stream per stream) when it starts and gives it
+  // back when it ends.
+  uint4 *bndH;                // [nslots][bnd_cta] bottom H of a pass (only when npass > 1)
   uint4 *bndF;
+  int *slot_flags;            // [nslots] 0 = free
+  int nslots;
+  long long bnd_cta, bnd_stream;
   int nq;                     // table rows in use (distinct query symbols)
   int npass;
   u32 negq;                   // both lanes: -(gap open + extend) in the mode's encoding
@@ -146,6 +152,23 @@ __device__ __forceinline__ u32 swb_pack16(u32 lo, u32 hi)
   u32 r;
   asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(hi), "r"(lo));
   return r;
+}
+
+// Multi-pass scratch: claim / release a region (see ScanParams::slot_flags).  One thread per CTA calls these.
+__device__ __forceinline__ int swb_claim_slot(const ScanParams &P)
+{
+  int s = (int)((blockIdx.x + blockIdx.y * gridDim.x) % (unsigned)P.nslots);
+  for (long long probes = 0;; probes++)
+  {
+    if (atomicCAS(P.slot_flags + s, 0, 1) == 0) return s;
+    s = s + 1 == P.nslots ? 0 : s + 1;
+    if (probes > (1ll << 26)) __trap();            // more CTAs resident than regions: never hang the GPU
+  }
+}
+__device__ __forceinline__ void swb_release_slot(const ScanParams &P, int s)
+{
+  __threadfence();
+  atomicExch(P.slot_flags + s, 0);
 }
 
 // One DP cell for both lanes.  hd = H(i-1,j-1), s = score word, e = E(i,j), f = F(i,j).
@@ -303,7 +326,13 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
   const long long b0 = S.pairblk[p0];
   const int nblk = (int)(S.pairblk[p1] - b0);
   const uint2 *blk = S.blocks + b0;
-  const long long bnd0 = S.bnd_base + b0;
+  __shared__ int bnd_slot;
+  if (MP)
+  {
+    if (tid == 0) bnd_slot = swb_claim_slot(P);
+    __syncthreads();
+  }
+  const long long bnd0 = MP ? (long long)bnd_slot * P.bnd_cta + (long long)k * P.bnd_stream : 0;
   const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);   // every warp holds all 8 streams
   const int nsteps = nblk_max > 0 ? nblk_max + G - 1 : 0;
   const u32 negq = (KQ | KR) ? KQ : P.negq, negr = (KQ | KR) ? KR : P.negr;
@@ -477,6 +506,11 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
       b++;
     }
   }
+  if (MP)
+  {
+    __syncthreads();
+    if (tid == 0) swb_release_slot(P, bnd_slot);
+  }
 }
 
 // ---- scan kernel, second geometry: one warp = one pipeline stage of 32 streams -----------------------
@@ -559,7 +593,13 @@ __global__ void __launch_bounds__(SWB2_STREAMS * G, 16 / G) swb_scan2_kernel(con
   const long long b0 = S.pairblk[p0];
   const int nblk = (int)(S.pairblk[p1] - b0);
   const uint2 *blk = S.blocks + b0;
-  const long long bnd0 = S.bnd_base + b0;
+  __shared__ int bnd_slot;
+  if (MP)
+  {
+    if (tid == 0) bnd_slot = swb_claim_slot(P);
+    __syncthreads();
+  }
+  const long long bnd0 = MP ? (long long)bnd_slot * P.bnd_cta + (long long)lane * P.bnd_stream : 0;
   const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);   // every warp holds all 32 streams
   const int nsteps = nblk_max > 0 ? nblk_max + G - 1 : 0;
   const u32 negq = (KQ | KR) ? KQ : P.negq, negr = (KQ | KR) ? KR : P.negr;
@@ -731,6 +771,12 @@ __global__ void __launch_bounds__(SWB2_STREAMS * G, 16 / G) swb_scan2_kernel(con
       par ^= SWB2_XFER;
       b++;
     }
+  }
+  if (MP)
+  {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");       // (stage 0's last prefetch, if any)
+    __syncthreads();
+    if (tid == 0) swb_release_slot(P, bnd_slot);
   }
 }
 

@@ -240,6 +240,7 @@ struct swb_db
   DevBuf<unsigned long long> counters;       // [0] requeue count, [1..3] width counts
   DevBuf<unsigned char> he;
   DevBuf<uint4> bndH, bndF;
+  DevBuf<int> slot_flags;         // multi-pass scratch regions in use (ScanParams::slot_flags)
   DevBuf<ScanSeg> segs;           // chunk table of a merged (whole-shard) scan launch
   DevBuf<unsigned> hist;          // [SWB_HIST_BINS] admissible scores, [SWB_HIST_BINS] = the cut bin
   DevBuf<unsigned long long> cand, cand_sorted;   // score << 32 | subject of the candidates
@@ -734,13 +735,19 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       ScanSeg &S = segs[k];
       S.blocks = L->blocks.p; S.pairblk = L->pairblk.p; S.stream_pair = L->stream_pair.p;
       S.pair_scores = L->pair_scores.p;
-      S.bnd_base = sum_blocks;
-      sum_blocks += L->cap_blocks;
+      sum_blocks = std::max(sum_blocks, L->cap_blocks);
     }
+    // multi-pass scratch: one region per resident CTA (ScanParams::slot_flags), each holding the longest
+    // stream any chunk can give it: an equal share of the chunk's blocks plus one pair's worth of slack
+    const int nslots = db->sm_count * occ;
+    const long long bnd_stream = sum_blocks / nstreams + (db->longest + 3) / 4 + 2;
+    const long long bnd_cta = bnd_stream * cta_streams;
     if (npass > 1)
     {
-      SWB_TRY(db->bndH.reserve((size_t)sum_blocks));
-      SWB_TRY(db->bndF.reserve((size_t)sum_blocks));
+      SWB_TRY(db->bndH.reserve((size_t)nslots * (size_t)bnd_cta));
+      SWB_TRY(db->bndF.reserve((size_t)nslots * (size_t)bnd_cta));
+      SWB_TRY(db->slot_flags.reserve((size_t)nslots));
+      SWB_CUDA(cudaMemsetAsync(db->slot_flags.p, 0, (size_t)nslots * sizeof(int), st));
     }
     SWB_TRY(db->segs.reserve(std::max<size_t>(segs.size(), 1)));
     if (!segs.empty())
@@ -754,6 +761,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     memset(&P, 0, sizeof P);
     P.m16 = db->m16.p; P.qrow_off = db->qrow_off.p;
     P.bndH = db->bndH.p; P.bndF = db->bndF.p;
+    P.slot_flags = db->slot_flags.p; P.nslots = nslots; P.bnd_cta = bnd_cta; P.bnd_stream = bnd_stream;
     P.nq = tb.nq; P.npass = npass;
     P.negq = nq16 | (nq16 << 16); P.negr = nr16 | (nr16 << 16); P.padword = pad16 | (pad16 << 16);
     P.stagger = stagger;
@@ -871,16 +879,22 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       SWB_CUDA(cudaGetLastError());
       L2.stream_pair_n = nstreams16;
       SWB_CUDA(cudaMemsetAsync(L2.pair_scores.p, 0, (size_t)L2.npairs * sizeof(u32), st));
+      const int nslots16 = db->sm_count * occ16;
+      const long long bnd_stream16 = L2.cap_blocks / nstreams16 + (db->longest + 3) / 4 + 2;
       if (np16 > 1)
       {
-        SWB_TRY(db->bndH.reserve((size_t)L2.cap_blocks));
-        SWB_TRY(db->bndF.reserve((size_t)L2.cap_blocks));
+        SWB_TRY(db->bndH.reserve((size_t)nslots16 * (size_t)bnd_stream16 * (size_t)streams16));
+        SWB_TRY(db->bndF.reserve((size_t)nslots16 * (size_t)bnd_stream16 * (size_t)streams16));
+        SWB_TRY(db->slot_flags.reserve((size_t)nslots16));
+        SWB_CUDA(cudaMemsetAsync(db->slot_flags.p, 0, (size_t)nslots16 * sizeof(int), st));
       }
       ScanParams P2;
       memset(&P2, 0, sizeof P2);
       P2.seg.blocks = L2.blocks.p; P2.seg.pairblk = L2.pairblk.p; P2.seg.stream_pair = L2.stream_pair.p;
-      P2.seg.pair_scores = L2.pair_scores.p; P2.seg.bnd_base = 0;
+      P2.seg.pair_scores = L2.pair_scores.p;
       P2.m16 = db->m16.p; P2.qrow_off = db->qrow_off.p; P2.bndH = db->bndH.p; P2.bndF = db->bndF.p;
+      P2.slot_flags = db->slot_flags.p; P2.nslots = nslots16; P2.bnd_stream = bnd_stream16;
+      P2.bnd_cta = bnd_stream16 * streams16;
       P2.nq = t16.nq; P2.npass = np16;
       const unsigned q16 = (unsigned)(unsigned short)enc16(-sc->gap_open_extend, SWB_MODE_INT16);
       const unsigned r16 = (unsigned)(unsigned short)(short)(-sc->gap_extend);
@@ -1182,7 +1196,7 @@ int batch_impl(swb_db *db, int nqueries, const uint8_t *const *queries, const in
       SWB_CUDA(cudaMemsetAsync(L->pair_scores.p, 0, (size_t)L->npairs * (size_t)m * sizeof(u32), st));
       ScanSeg &S = segs[c];
       S.blocks = L->blocks.p; S.pairblk = L->pairblk.p; S.stream_pair = L->stream_pair.p;
-      S.pair_scores = L->pair_scores.p; S.bnd_base = 0; S.score_stride = L->npairs;
+      S.pair_scores = L->pair_scores.p; S.score_stride = L->npairs;
     }
     SWB_TRY(db->m16.reserve(SWB_M16_BYTES / sizeof(short)));
     SWB_TRY(db->qrow_off.reserve(qrow.size()));
@@ -1827,6 +1841,7 @@ int swb_db_close(swb_db *db)
   db->scores.release(); db->bestpos.release(); db->bestq.release(); db->requeue.release();
   db->list.release(); db->counters.release(); db->he.release(); db->bndH.release();
   db->bndF.release(); db->segs.release();
+  db->slot_flags.release();
   db->hist.release(); db->cand.release(); db->cand_sorted.release(); db->sort_tmp.release();
   for (int i = 0; i < 4; i++)
     if (db->ev[i]) cudaEventDestroy(db->ev[i]);
