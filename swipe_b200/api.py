@@ -59,7 +59,7 @@ def load_library():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.build_lib()
+    path = os.environ.get("SWB_LIBRARY") or _build.build_lib()       # (an experiment build, tools/build_variant.sh)
     if not os.path.exists(path):
         raise RuntimeError("swipe_b200: %s is not built (run python -m swipe_b200.build)" % path)
     lib = C.CDLL(path)

@@ -34,6 +34,9 @@ typedef unsigned long long u64;
 #define SWB_M16_BYTES 2256    // its image in global memory: 33 * 34 halfwords padded to a multiple of 16 B
 #define SWB_FLAG_START 1u
 #define SWB_FLAG_END 2u
+#ifndef SWB_BUILD_BATCH
+#define SWB_BUILD_BATCH 1    // table rows whose loads are in flight together (geometry 1); > 1 is an experiment
+#endif
 
 enum { SWB_MODE_INT16 = 0, SWB_MODE_HYBRID = 1 };
 
@@ -362,10 +365,31 @@ __global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const
     const u32 da = bsrc + ((blkw.x >> bshift) & 63u) * (2u * SWB_MS_STRIDE);
     const u32 db = bsrc + ((blkw.y >> bshift) & 63u) * (2u * SWB_MS_STRIDE);
     const u32 dst = bdst + slot_off;
+    // (SWB_BUILD_BATCH > 1, experiment: the loads of several rows issued back to back so that their
+    // latencies overlap -- a fifth of the kernel's stall samples sit in these few instructions -- at the
+    // price of registers the tile can hardly spare)
+#if SWB_BUILD_BATCH == 1
 #pragma unroll
     for (int j = 0; j < NBJ; j++)
       if (bmask & (1u << j))
         swb_sts32(dst + j * RG * 128, swb_pack16(swb_lds16(da + j * RG * 2), swb_lds16(db + j * RG * 2)));
+#else
+#pragma unroll
+    for (int j = 0; j < NBJ; j += SWB_BUILD_BATCH)
+    {
+      u32 lo[SWB_BUILD_BATCH], hi[SWB_BUILD_BATCH];
+#pragma unroll
+      for (int u = 0; u < SWB_BUILD_BATCH; u++)
+        if (j + u < NBJ && (bmask & (1u << (j + u))))
+        {
+          lo[u] = swb_lds16(da + (j + u) * RG * 2);
+          hi[u] = swb_lds16(db + (j + u) * RG * 2);
+        }
+#pragma unroll
+      for (int u = 0; u < SWB_BUILD_BATCH; u++)
+        if (j + u < NBJ && (bmask & (1u << (j + u)))) swb_sts32(dst + (j + u) * RG * 128, swb_pack16(lo[u], hi[u]));
+    }
+#endif
     if (g == 0) swb_sts32(hdr + slot_off, (blkw.x >> 6) & 3u);
   };
 
