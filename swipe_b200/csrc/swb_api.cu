@@ -722,7 +722,7 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     if (merge && resident && !getenv("SWB_OVERSUB")) oversub = work.size() >= 4 ? 1 : oversub;
     const int grid = db->sm_count * occ * oversub;
     const int nstreams = grid * cta_streams;
-    long long sum_blocks = 0;
+    long long sum_blocks = 0, all_blocks = 0;
     std::vector<ScanSeg> segs(work.size());
     for (size_t k = 0; k < work.size(); k++)
     {
@@ -735,19 +735,31 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       ScanSeg &S = segs[k];
       S.blocks = L->blocks.p; S.pairblk = L->pairblk.p; S.stream_pair = L->stream_pair.p;
       S.pair_scores = L->pair_scores.p;
+      S.bnd_base = all_blocks;
+      all_blocks += L->cap_blocks;
       sum_blocks = std::max(sum_blocks, L->cap_blocks);
     }
-    // multi-pass scratch: one region per resident CTA (ScanParams::slot_flags), each holding the longest
-    // stream any chunk can give it: an equal share of the chunk's blocks plus one pair's worth of slack
-    const int nslots = db->sm_count * occ;
-    const long long bnd_stream = sum_blocks / nstreams + (db->longest + 3) / 4 + 2;
-    const long long bnd_cta = bnd_stream * cta_streams;
+    // Multi-pass scratch (ScanParams::bndH): one entry per block of the shard while that fits the budget
+    // (SWB_BND_BUDGET_MB, default 64 GiB: the faster layout, 4 x the shard's own size), else one region per
+    // resident CTA, each holding the longest stream any chunk can give it: an equal share of the chunk's
+    // blocks plus one pair's worth of slack.
+    long long bnd_budget = 64ll << 30;
+    if (const char *env = getenv("SWB_BND_BUDGET_MB")) bnd_budget = std::max<long long>(0, atoll(env)) << 20;
+    int nslots = 0;
+    long long bnd_stream = 0, bnd_cta = 0;
     if (npass > 1)
     {
-      SWB_TRY(db->bndH.reserve((size_t)nslots * (size_t)bnd_cta));
-      SWB_TRY(db->bndF.reserve((size_t)nslots * (size_t)bnd_cta));
-      SWB_TRY(db->slot_flags.reserve((size_t)nslots));
-      SWB_CUDA(cudaMemsetAsync(db->slot_flags.p, 0, (size_t)nslots * sizeof(int), st));
+      if (2 * all_blocks * (long long)sizeof(uint4) > bnd_budget)
+      {
+        nslots = db->sm_count * occ;
+        bnd_stream = sum_blocks / nstreams + (db->longest + 3) / 4 + 2;
+        bnd_cta = bnd_stream * cta_streams;
+        SWB_TRY(db->slot_flags.reserve((size_t)nslots));
+        SWB_CUDA(cudaMemsetAsync(db->slot_flags.p, 0, (size_t)nslots * sizeof(int), st));
+      }
+      const size_t entries = nslots ? (size_t)nslots * (size_t)bnd_cta : (size_t)all_blocks;
+      SWB_TRY(db->bndH.reserve(entries));
+      SWB_TRY(db->bndF.reserve(entries));
     }
     SWB_TRY(db->segs.reserve(std::max<size_t>(segs.size(), 1)));
     if (!segs.empty())

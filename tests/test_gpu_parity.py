@@ -471,3 +471,20 @@ def test_end_cells_every_query_length(oracle, qlen):
     for k in sel:
         es, ed, eq = oracle.score_end(residues[offsets[k]:offsets[k + 1]], q, B62, 11, 1)
         assert (s[k], bp[k], bq[k]) == (es, ed, eq), "subject %d (len %d)" % (k, offsets[k + 1] - offsets[k])
+
+
+@pytest.mark.parametrize("geometry", [1, 2])
+def test_multi_pass_scratch_sized_for_resident_ctas(oracle, monkeypatch, geometry):
+    """Shards whose full pass-boundary scratch (32 B per block) would not fit use one region per resident
+    CTA, claimed when the CTA starts and released when it ends (ScanParams::slot_flags).  Forced here with a
+    zero budget, over several chunks so that regions are reused by later CTAs."""
+    monkeypatch.setenv("SWB_BND_BUDGET_MB", "0")
+    monkeypatch.setenv("SWB_CHUNK_BYTES", "150000")
+    q = synth.protein_query(1100, seed=20261017 + 1100)
+    residues, offsets = synth.protein_db(4000, query=q, seed=1102, plant_every=40, max_len=1400)
+    exp = oracle.scan(residues, offsets, q, B62, 11, 1)[0]
+    with Database(residues, offsets) as db:
+        db.set_geometry(geometry)
+        got = db.search(q, Scoring(B62, 11, 1))
+        assert db.last_counters["scan_passes"] > 1
+    assert np.array_equal(got, exp)

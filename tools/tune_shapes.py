@@ -25,7 +25,7 @@ with Database(residues, offsets) as db:
         for lane_mode in modes:
             for (G, R) in shapes:
                 npass = -(-qlen // (G * R))
-                if npass > 3 and qlen > 200 and geom == 1:
+                if npass > 16 and qlen > 200 and geom == 1:
                     continue
                 db.set_shape(G, R, lane_mode)
                 best = 1e9
