@@ -269,8 +269,11 @@ __host__ __device__ inline size_t swb_scan_smem(int G, int nq)
 // KQ / KR != 0: gap penalties compiled in as immediates (both lanes, the mode's encoding) -- the DPX and
 // fp16 ops then read one register less each, which is worth ~4 % of the inner loop
 // (profiles/r1_ubench_tile_v2.txt, "immediate penalties"); 0 / 0 = read them from ScanParams.
+#ifndef SWB_MIN_CTAS
+#define SWB_MIN_CTAS(G) (64 / (G))       // CTAs per SM the register allocation is held to (experiments override)
+#endif
 template <int G, int R, int MODE, bool MP, u32 KQ = 0, u32 KR = 0>
-__global__ void __launch_bounds__(SWB_STREAMS * G, 64 / G) swb_scan_kernel(const ScanParams P)
+__global__ void __launch_bounds__(SWB_STREAMS * G, SWB_MIN_CTAS(G)) swb_scan_kernel(const ScanParams P)
 {
   extern __shared__ uint4 smem4[];
   const u32 sbase = (u32)__cvta_generic_to_shared(smem4);     // staged score matrix at sbase
