@@ -488,3 +488,17 @@ def test_multi_pass_scratch_sized_for_resident_ctas(oracle, monkeypatch, geometr
         got = db.search(q, Scoring(B62, 11, 1))
         assert db.last_counters["scan_passes"] > 1
     assert np.array_equal(got, exp)
+
+
+def test_device_sink_wide_cells(oracle):
+    """A scoring system that needs 64-bit cells (penalties beyond 2^30) cannot use the 32-bit score half
+    of a candidate key: swb_search_hits then reads the scores back and runs the host sink inside the
+    library -- same list."""
+    q = synth.protein_query(60, seed=81)
+    residues, offsets = synth.protein_db(300, query=q, seed=82, plant_every=10, max_len=200)
+    sc = Scoring(B62, 2 ** 31, 2 ** 31)
+    exp = oracle.scan(residues, offsets, q, B62, 2 ** 31, 2 ** 31)[0]
+    oseq, osc, otot, oobv = oracle.topk(np.arange(exp.size), exp, 20, min_score=1)
+    with Database(residues, offsets) as db:
+        seq, s, tot, obv = db.search_hits(q, sc, 20, 1)
+    assert np.array_equal(seq, oseq) and np.array_equal(s, osc) and (tot, obv) == (otot, oobv)

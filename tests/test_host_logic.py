@@ -118,3 +118,14 @@ def test_hits_merge_equals_the_dense_sink(oracle):
     assert swipe_b200.hits_merge(lists, 0)[0].size == 0
     short, _ = swipe_b200.hits_merge([(np.array([7, 3]), np.array([9, 9]))], 10)
     assert short.tolist() == [7, 3]
+
+
+def test_batch_and_sink_argument_checks_do_not_need_a_gpu():
+    lib = swipe_b200.load_library()
+    n = ctypes.c_int64()
+    assert lib.swb_search_hits(None, None, 0, None, 0, 10, 1, 100, None, None, ctypes.byref(n), None, None, None) == -1
+    assert lib.swb_search_batch(None, 1, None, None, None, None, None) == -1
+    assert lib.swb_search_hits_batch(None, -1, None, None, None, 0, 1, 0, 0, None, None, None, None, None, None) == -1
+    assert lib.swb_set_cache_limit(-5) == -1 and lib.swb_set_cache_limit(8 << 30) == 0
+    assert lib.swb_set_geometry(None, 1) == -1
+    assert lib.swb_alu_peak(0, None, None) == -1
