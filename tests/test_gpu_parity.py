@@ -37,7 +37,7 @@ def test_known_answers(oracle):
         assert db.search(q, Scoring(B62, 11, 1)).tolist() == [17, 62, 11, 62, 0, 46]
 
 
-@pytest.mark.parametrize("shape", [(0, 0, -1), (8, 8, 0), (8, 13, 1), (16, 24, 0), (16, 24, 1),
+@pytest.mark.parametrize("shape", [(0, 0, -1), (4, 25, 1), (4, 25, 0), (8, 8, 0), (8, 13, 1), (16, 24, 0), (16, 24, 1),
                                    (32, 12, 0), (32, 12, 1), (32, 32, 1)])
 def test_edge_cases_all_shapes(oracle, shape):
     q = synth.protein_query(375)
@@ -393,7 +393,7 @@ def _mp_case(oracle):
     return _MP
 
 
-SHAPES = [(8, 8), (8, 13), (8, 16), (16, 12), (16, 16), (16, 20), (16, 24), (32, 12), (32, 16),
+SHAPES = [(4, 25), (8, 8), (8, 13), (8, 16), (16, 12), (16, 16), (16, 20), (16, 24), (32, 12), (32, 16),
           (32, 20), (32, 24), (32, 28), (32, 32)]
 
 

@@ -6,7 +6,7 @@ from swipe_b200 import Database, Scoring, scoring, synth
 
 nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 2000000
 qlens = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [375]
-shapes = [(8, 8), (8, 13), (8, 16), (16, 12), (16, 16), (16, 20), (16, 24), (32, 12), (32, 16),
+shapes = [(4, 25), (8, 8), (8, 13), (8, 16), (16, 12), (16, 16), (16, 20), (16, 24), (32, 12), (32, 16),
           (32, 20), (32, 24), (32, 28), (32, 32)]
 if len(sys.argv) > 3:
     shapes = [tuple(int(v) for v in x.split("x")) for x in sys.argv[3].split(",")]
