@@ -403,7 +403,7 @@ struct ShapeEntry { int G, R, mode; scan_fn fn, fn_mp; u32 kq, kr; int geom; }; 
 #define SWB_SHAPE2(G, R) SWB_SHAPE_OF(swb_scan2_kernel, 2, G, R)
 
 const ShapeEntry g_shapes[] = {
-    SWB_SHAPE(4, 25),  // one warp per CTA: four stages x eight streams, no inter-warp hand-off at all
+    SWB_SHAPE(4, 25),  // one warp per CTA, no inter-warp hand-off at all: measured SLOWER (4.3 TCUPS at 100 aa: the lone warp builds every table itself); kept for the comparison
     SWB_SHAPE(8, 8),   SWB_SHAPE(8, 13),  SWB_SHAPE(8, 16),  SWB_SHAPE(16, 12), SWB_SHAPE(16, 16),
     SWB_SHAPE(16, 20), SWB_SHAPE(16, 24), SWB_SHAPE(32, 12), SWB_SHAPE(32, 16), SWB_SHAPE(32, 20),
     SWB_SHAPE(32, 24), SWB_SHAPE(32, 28), SWB_SHAPE(32, 32),
@@ -421,7 +421,7 @@ const ShapeEff g_eff[] = {
     // geometry 1: r1 table scaled by what the round-2 row loop / boundary prefetch measured (x 1.025 single
     // pass, x 1.037 multi-pass), with the shapes re-measured in round 2 entered as measured
     // (profiles/r2_tune_shapes.txt)
-    {1, 4, 25, 5.6, 4.5},  {1, 8, 8, 5.12, 0},     {1, 8, 13, 5.70, 0},    {1, 8, 16, 6.15, 0},    {1, 16, 12, 6.58, 0},   {1, 16, 16, 7.22, 0},
+    {1, 4, 25, 4.31, 3.5},  {1, 8, 8, 5.12, 0},     {1, 8, 13, 5.70, 0},    {1, 8, 16, 6.15, 0},    {1, 16, 12, 6.58, 0},   {1, 16, 16, 7.22, 0},
     {1, 16, 20, 7.27, 0},  {1, 16, 24, 7.61, 6.41}, {1, 32, 12, 6.52, 5.92}, {1, 32, 16, 6.81, 6.68}, {1, 32, 20, 6.97, 6.99},
     {1, 32, 24, 7.69, 6.69}, {1, 32, 28, 7.57, 6.65}, {1, 32, 32, 6.36, 6.62},
     // geometry 2 (measured): only ahead for short queries, where its four-stage CTA amortises the table build
