@@ -721,6 +721,10 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
       resident = true;
     }
     if (merge && resident && !getenv("SWB_OVERSUB")) oversub = work.size() >= 4 ? 1 : oversub;
+    // a shard that is still arriving is scanned chunk group by chunk group anyway: one CTA per resident slot
+    // and chunk keeps the streams of its small first chunks as long as possible (measured: 15.2 -> 14.5 ms end
+    // to end for an eighth of the 5 M database, 97.3 -> 96.4 ms for all of it)
+    if (!resident && !getenv("SWB_OVERSUB")) oversub = 1;
     const int grid = db->sm_count * occ * oversub;
     const int nstreams = grid * cta_streams;
     long long sum_blocks = 0, all_blocks = 0;
@@ -1496,8 +1500,14 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
   // a small shard (one GPU's share of a database spread over eight) is still cut into about four chunks:
   // the scan then runs as several waves of CTAs whose ragged ends overlap (measured on a 0.6 M-subject
   // shard: 11.95 -> 11.68 ms)
-  if (wait && getenv("SWB_CHUNK_BYTES") == nullptr && nsrc > 0 && cut_off[nsrc] < 4 * chunk_bytes)
-    chunk_bytes = std::max<long long>(32LL << 20, cut_off[nsrc] / 4 + 1);
+  // A shard that is still arriving is cut into about eight chunks (32 to 256 MB): the scan of the LAST chunk
+  // cannot start before the upload ends, so it must be a small part of the whole -- with the 256 MB chunks of
+  // a big shard, one GPU's eighth of the database ended in a chunk holding more than half of it.
+  if (getenv("SWB_CHUNK_BYTES") == nullptr && nsrc > 0)
+  {
+    if (wait && cut_off[nsrc] < 4 * chunk_bytes) chunk_bytes = std::max<long long>(32LL << 20, cut_off[nsrc] / 4 + 1);
+    if (!wait) chunk_bytes = std::min<long long>(chunk_bytes, std::max<long long>(32LL << 20, cut_off[nsrc] / 8 + 1));
+  }
   std::vector<long long> cut;                       // chunk c covers source sequences [cut[c], cut[c+1])
   cut.push_back(0);
   // asynchronous open: the first chunks are small so that the scan can start while most of the shard
@@ -1507,7 +1517,7 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
   {
     const long long lo = cut.back();
     long long budget = chunk_bytes;
-    if (ramp && cut.size() <= 3) budget = chunk_bytes >> (4 - cut.size());
+    if (ramp && cut.size() <= 3) budget = std::min<long long>(chunk_bytes, (32LL << 20) << (cut.size() - 1));
     const long long *e = std::upper_bound(cut_off + lo + 1, cut_off + nsrc + 1, cut_off[lo] + budget);
     long long hi = (long long)(e - cut_off) - 1;     // last boundary within the byte budget
     if (hi <= lo) hi = lo + 1;
