@@ -33,6 +33,33 @@ with Database(res, off) as db:
     print("protein ok", int(a.max()), db.last_counters)
 with Database(res, off, wait=False) as db:
     assert np.array_equal(db.search(q, sc), a)
+# round 2: the second kernel geometry (single pass, multi-pass with the cp.async feed, per-CTA scratch regions),
+# the device sink, batched queries, the warp-per-subject end-cell kernel in passes
+with Database(res, off) as db:
+    db.set_geometry(2)
+    assert np.array_equal(db.search(q[:375], sc), Database(res, off).search(q[:375], sc))
+    assert np.array_equal(db.search(q, sc), a)          # 500 rows: two passes of G16
+    db.set_shape(4, 25, 1)
+    assert np.array_equal(db.search(q, sc), a)          # five passes of the four-stage CTA
+    db.set_shape(0, 0, -1)
+    os.environ["SWB_BND_BUDGET_MB"] = "0"
+    assert np.array_equal(db.search(q, sc), a)          # regions claimed / released per CTA
+    db.set_geometry(1)
+    db.set_shape(8, 8, 1)
+    assert np.array_equal(db.search(q, sc), a)
+    db.set_shape(0, 0, -1)
+    del os.environ["SWB_BND_BUDGET_MB"]
+    db.set_geometry(0)
+    seq, hs, tot, obv = db.search_hits(q, sc, 25, 1)
+    order = np.lexsort((-np.arange(a.size), -a))[:25]
+    assert np.array_equal(seq, order) and np.array_equal(hs, a[order])
+    qs = [q[:90], q[100:160], q[200:330], q[:25]]
+    got = db.search_batch(qs, sc)
+    for qq, g in zip(qs, got):
+        assert np.array_equal(g, db.search(qq, sc))
+    long_q = synth.protein_query(1300, seed=9)
+    s1, bp1, bq1 = db.search_end(long_q, sc, np.arange(0, 400, 25))     # two passes of 1024 rows
+    print("round-2 paths ok", int(hs[0]), int(s1.max()))
 tmp = tempfile.mkdtemp()
 qn = synth.dna_query(200, seed=5)
 rng = np.random.default_rng(1)
