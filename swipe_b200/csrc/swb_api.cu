@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1465,8 +1466,23 @@ struct OpenSrc
   const uint8_t *ttable = nullptr;        // [4096]
 };
 
+// SWB_TRACE_OPEN=1: host-side timeline of an open on stderr (tuning aid)
+struct OpenTrace
+{
+  bool on = getenv("SWB_TRACE_OPEN") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char *what)
+  {
+    if (!on) return;
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[swb open] %8.1f us  %s\n", us, what);
+  }
+};
+
 static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wait)
 {
+  OpenTrace trace;
+  trace.mark("open_impl");
   const long long nseq = S.nseq;
   const long long *offsets = S.offsets;
   int ndev = 0;
@@ -1541,6 +1557,7 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
     for (int i = 0; i < 3; i++) SWB_CUDA(cudaEventCreate(&db->ev_open[i]));
     for (int i = 0; i < 2; i++) SWB_CUDA(cudaEventCreate(&db->ev_batch[i]));
     SWB_CUDA(cudaEventCreateWithFlags(&db->ev_uploaded, cudaEventDisableTiming));
+    trace.mark("streams and events created");
     SWB_TRY(db->residues.reserve((size_t)offsets[nseq] + 16));
     SWB_TRY(db->offsets.reserve((size_t)nseq + 1));
     SWB_CUDA(cudaEventRecord(db->ev_open[0], db->copy_stream));
@@ -1630,6 +1647,7 @@ static int open_impl(int device, OpenSrc &S, void *stream, swb_db **out, bool wa
       SWB_CUDA(cudaStreamWaitEvent(db->copy_stream, done, 0));
       SWB_CUDA(cudaEventDestroy(done));
     }
+    trace.mark("all chunks enqueued");
     SWB_CUDA(cudaEventRecord(db->ev_uploaded, db->copy_stream));
     SWB_CUDA(cudaEventRecord(db->ev_open[2], db->layout_stream));
     if (db->chunks.empty()) SWB_CUDA(cudaEventRecord(db->ev_open[1], db->layout_stream));
