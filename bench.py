@@ -387,7 +387,7 @@ def main():
     pin_res.u8[:sh_res] = w.residues[w.offsets[lo]: w.offsets[hi]]
     pin_off = HostBuffer(8 * (sh_nseq + 1))
     pin_off.view(np.int64)[:] = sh_off
-    if cfg["kind"] == "nt":
+    if cfg["kind"] == "nt" and world == 1:
         w.residues = None                               # the pinned copy is the database from here on
 
     stream = torch.cuda.Stream()
