@@ -64,6 +64,8 @@ class HitExchange:
             self.mine, self.all = self.mine.pin_memory(), self.all.pin_memory()
             self.mine_dev = torch.empty(shape, dtype=torch.int64, device=device)
             self.all_dev = [torch.empty(shape, dtype=torch.int64, device=device) for _ in range(self.world)]
+        self.mine.fill_(-1)
+        self.mine_np, self.all_np = self.mine.numpy(), self.all.numpy()
 
     def __call__(self, lists):
         """lists: this rank's [(seqnos, scores)] * nlists.  Returns the merged (seqnos, scores) on rank 0,
@@ -71,11 +73,14 @@ class HitExchange:
         torch, dist = self.torch, self.dist
         if self.world == 1:
             return hits_merge(lists, self.keep) if len(lists) > 1 else lists[0]
-        self.mine.fill_(-1)
+        mine = self.mine_np                              # numpy view of the (pinned) staging tensor
         for k, (seq, sc) in enumerate(lists):
             n = len(seq)
-            self.mine[k * self.keep: k * self.keep + n, 0] = torch.from_numpy(np.ascontiguousarray(seq, dtype=np.int64))
-            self.mine[k * self.keep: k * self.keep + n, 1] = torch.from_numpy(np.ascontiguousarray(sc, dtype=np.int64))
+            base = k * self.keep
+            mine[base: base + n, 0] = seq
+            mine[base: base + n, 1] = sc
+            if n < self.keep:
+                mine[base + n, 0] = -1                   # end marker: a list is sorted, so the first -1 ends it
         if self.device is not None:
             ctx = torch.cuda.stream(self.stream) if self.stream is not None else torch.cuda.stream(torch.cuda.current_stream())
             with ctx:
@@ -92,12 +97,13 @@ class HitExchange:
                 self.all[r].copy_(parts[r])
         if self.rank != 0:
             return None
-        g = self.all.numpy()
+        g = self.all_np
         parts = []
         for r in range(self.world):
             for k in range(self.nlists):
                 blk = g[r, k * self.keep: (k + 1) * self.keep]
-                n = int((blk[:, 0] >= 0).sum())
+                neg = np.flatnonzero(blk[:, 0] < 0)
+                n = int(neg[0]) if neg.size else self.keep
                 parts.append((blk[:n, 0], blk[:n, 1]))
         return hits_merge(parts, self.keep)
 
