@@ -113,3 +113,30 @@ def test_oracle_matches_reference_cli(oracle):
     a, _, _ = oracle.scan(res, off, qn, m, 5, 2)
     b, _, _ = oracle.scan(res, off, synth.revcomp_nt(qn), m, 5, 2)
     assert np.array_equal(np.sort(np.stack([a, b], 1), 1), gn["strand_scores_sorted"])
+
+
+def test_vectorised_writers_equal_the_per_sequence_ones(tmp_path):
+    """bench.py's reference arm writes its sample with the vectorised writers: they must produce the very
+    files the per-sequence writers (the ones pinned against the reference program) produce."""
+    q = synth.protein_query(120)
+    res, off = synth.protein_db(700, query=q, seed=5, plant_every=50, max_len=400)
+    subs = [res[off[i]:off[i + 1]] for i in range(700)]
+    a, b = str(tmp_path / "slow"), str(tmp_path / "fast")
+    s1 = blastdb.write_protein(a, subs)
+    s2 = blastdb.write_protein_fast(b, res, off)
+    assert np.array_equal(s1, s2)
+    assert open(a + ".psq", "rb").read() == open(b + ".psq", "rb").read()
+    with BlastDB(b) as db:
+        assert db.nseq == 700 and db.symbols == int(off[-1])
+        assert np.array_equal(db.sequence(123), subs[123])
+    qn = synth.dna_query(300)
+    r, o = synth.dna_db_planted(900, qn, seed=6, plant_every=40, ambiguity_every=2)
+    nsubs = [r[o[i]:o[i + 1]] for i in range(900)]
+    a, b = str(tmp_path / "nslow"), str(tmp_path / "nfast")
+    s1, a1 = blastdb.write_nucleotide(a, nsubs)
+    s2, a2 = blastdb.write_nucleotide_fast(b, r, o, chunk=250)
+    assert np.array_equal(s1, s2) and np.array_equal(a1, a2)
+    assert open(a + ".nsq", "rb").read() == open(b + ".nsq", "rb").read()
+    with BlastDB(b, nucleotide=True) as db:
+        for i in (0, 40, 80, 899):
+            assert np.array_equal(db.sequence(i), nsubs[i])

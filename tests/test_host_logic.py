@@ -129,3 +129,24 @@ def test_batch_and_sink_argument_checks_do_not_need_a_gpu():
     assert lib.swb_set_cache_limit(-5) == -1 and lib.swb_set_cache_limit(8 << 30) == 0
     assert lib.swb_set_geometry(None, 1) == -1
     assert lib.swb_alu_peak(0, None, None) == -1
+
+
+def test_residue_balanced_shard_cuts():
+    """shard_cuts: contiguous ranges covering every sequence once, each within one sequence of an equal
+    share of the residues -- the cut swipe-b200 -a N and bench.py --gpus N make."""
+    rng = np.random.default_rng(3)
+    lens = rng.integers(1, 5000, size=20000)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for world in (1, 2, 3, 4, 8):
+        cuts = shard.shard_cuts(off, world)
+        assert cuts[0][0] == 0 and cuts[-1][1] == lens.size
+        assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+        share = off[-1] / world
+        for a, b in cuts:
+            assert abs((off[b] - off[a]) - share) <= lens.max()
+    # more ranks than sequences: empty tail shards, nothing lost
+    tiny = shard.shard_cuts(np.array([0, 10, 30]), 4)
+    assert tiny[0][0] == 0 and tiny[-1][1] == 2 and sum(b - a for a, b in tiny) == 2
+    ex = shard.HitExchange(10, 2)                       # no process group: the single-rank path merges locally
+    seq, sc = ex([(np.array([5, 1]), np.array([9, 3])), (np.array([7]), np.array([9]))])
+    assert seq.tolist() == [7, 5, 1] and sc.tolist() == [9, 9, 3]
