@@ -74,3 +74,16 @@ def test_batch_nucleotide_and_generic_penalties(oracle):
             got = db.search_batch(qs, Scoring(m, *gaps))
         for k, qq in enumerate(qs):
             assert np.array_equal(got[k], oracle.scan(residues, offsets, qq, m, *gaps)[0]), (gaps, k)
+
+
+def test_batch_int16_lanes(oracle):
+    """Penalties beyond the fp16-pattern range (open + extend > 1023) put the scan on plain int16 lanes;
+    batched queries must take the same build."""
+    qs = _queries([80, 120, 60, 33], seed=70)
+    residues, offsets = synth.protein_db(1200, query=qs[1], seed=71, plant_every=30, max_len=600)
+    sc = Scoring(B62, 2000, 3)
+    with Database(residues, offsets) as db:
+        got = db.search_batch(qs, sc)
+        assert db.last_batch_counters[0]["scan_geometry"] == 2
+    for k, q in enumerate(qs):
+        assert np.array_equal(got[k], oracle.scan(residues, offsets, q, B62, 2000, 3)[0]), k
