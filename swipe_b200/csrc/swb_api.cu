@@ -476,7 +476,11 @@ int run_wide(swb_db *db, const long long *d_list, const long long *d_sel, long l
 {
   if (nsel == 0) return SWB_OK;
   cudaStream_t st = db->stream;
-  if (end && !use64 && getenv("SWB_NO_END_KERNEL") == nullptr)
+  // (a long query over very many subjects would want more pass-boundary scratch than is reasonable: that
+  // unusual combination stays on the one-thread-per-subject kernel below, which works in batches)
+  const bool end_scratch_ok = qlen <= 1024 ||
+                              (double)nsel * 2.0 * (double)std::max<long long>(db->longest, 1) * sizeof(int) <= 4e9;
+  if (end && !use64 && end_scratch_ok && getenv("SWB_NO_END_KERNEL") == nullptr)
   {
     // the alignment phase's few subjects: one warp each (swb_end_kernel), state in registers; queries
     // beyond 1024 rows go in passes with the pass boundary (2 ints per subject column) in scratch
