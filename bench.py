@@ -565,41 +565,45 @@ def main():
         # (the other ranks wait on the gloo group below: an NCCL barrier would spin a kernel on their GPUs,
         # which rank 0 is about to use from its own context)
         if rank == 0 and not args.no_product_path and torch.cuda.device_count() >= world:
-            cuts = shard_cuts(w.offsets, world)
-            dbs = []
-            for r, (a, b) in enumerate(cuts):
-                dbs.append((a, Database(w.residues[w.offsets[a]: w.offsets[b]],
-                                        (w.offsets[a: b + 1] - w.offsets[a]).astype(np.int64), device=r)))
-            out = [None] * world
+            try:
+                cuts = shard_cuts(w.offsets, world)
+                dbs = []
+                for r, (a, b) in enumerate(cuts):
+                    dbs.append((a, Database(w.residues[w.offsets[a]: w.offsets[b]],
+                                            (w.offsets[a: b + 1] - w.offsets[a]).astype(np.int64), device=r)))
+                out = [None] * world
 
-            def worker(r):
-                a, d = dbs[r]
-                ls = []
-                for s, q in enumerate(w.queries):
-                    seq, scv, _, _ = d.search_hits(q, sc, TOPK, 1, 2 ** 62, seqno_base=a)
-                    ls.append((seq * nq + s, scv))
-                out[r] = ls
+                def worker(r):
+                    a, d = dbs[r]
+                    ls = []
+                    for s, q in enumerate(w.queries):
+                        seq, scv, _, _ = d.search_hits(q, sc, TOPK, 1, 2 ** 62, seqno_base=a)
+                        ls.append((seq * nq + s, scv))
+                    out[r] = ls
 
-            def product_step():
-                th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
-                for t in th:
-                    t.start()
-                for t in th:
-                    t.join()
-                return hits_merge([l for ls in out for l in ls], TOPK)
-            for _ in range(2):
-                product_step()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                pm = product_step()
-            dt = time.perf_counter() - t0
-            for _, d in dbs:
-                d.close()
-            torch.cuda.set_device(local_rank)            # the handles switched this thread's device
-            product = {"value": w.cells * args.steps / dt * 1e-9, "unit": "GCUPS", "ms_per_step": dt * 1e3 / args.steps,
-                       "timing": "host wall clock around N threads (each search ends in a stream synchronize)",
-                       "topk_identical": bool(np.array_equal(pm[0], single[0]) and np.array_equal(pm[1], single[1])),
-                       "what": "one process, one host thread + swb_db handle per GPU, swb_search_hits + swb_hits_merge"}
+                def product_step():
+                    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+                    for t in th:
+                        t.start()
+                    for t in th:
+                        t.join()
+                    return hits_merge([l for ls in out for l in ls], TOPK)
+                for _ in range(2):
+                    product_step()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    pm = product_step()
+                dt = time.perf_counter() - t0
+                for _, d in dbs:
+                    d.close()
+                torch.cuda.set_device(local_rank)            # the handles switched this thread's device
+                product = {"value": w.cells * args.steps / dt * 1e-9, "unit": "GCUPS", "ms_per_step": dt * 1e3 / args.steps,
+                           "timing": "host wall clock around N threads (each search ends in a stream synchronize)",
+                           "topk_identical": bool(np.array_equal(pm[0], single[0]) and np.array_equal(pm[1], single[1])),
+                           "what": "one process, one host thread + swb_db handle per GPU, swb_search_hits + swb_hits_merge"}
+            except Exception as e:               # e.g. GPUs in exclusive-process mode: the other ranks own them
+                product = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.set_device(local_rank)
         dist.barrier(group=cpu_group)
         barrier()
 
