@@ -226,6 +226,14 @@ int swb_search_hits_batch(swb_db *db, int nqueries, const uint8_t *const *querie
                           int64_t upper_score, int64_t *const *out_seqno, int64_t *const *out_score,
                           int64_t *nhits, int64_t *totalhits, int64_t *obvious, swb_counters *counters);
 
+/* Subject filter of the device sink ("subject_filter all | bitmap | coded list"): bit (k & 7) of
+ * bitmap[k >> 3] says whether subject k may enter the hit list -- what db_check_inclusion decides per sequence
+ * for alias masks and taxid lists (swipe.cc:1373-1376, database.cc:687-733).  Excluded subjects are still
+ * scored (the scan streams the whole shard) but neither counted in totalhits / obvious nor admitted by
+ * swb_search_hits / swb_search_hits_batch; swb_search (dense scores) ignores the filter.  The bitmap is
+ * copied; NULL removes the filter.  A coded list is what swb_search_list takes.                          */
+int swb_db_set_filter(swb_db *db, const uint8_t *bitmap);
+
 /* Merges hit lists that are each in the sink's order (what swb_search_hits returns) into the best
  * `keep` overall -- the master's merge of the reference's MPI build (swipe.cc:1957-1974) and the
  * host-side step of a multi-GPU search.  Returns the number of hits written or a negative status. */

@@ -16,7 +16,7 @@ EXPORTS = ["swb_abi_version", "swb_align", "swb_alu_peak", "swb_blastdb_close", 
            "swb_blastdb_error", "swb_blastdb_header", "swb_blastdb_included", "swb_blastdb_info",
            "swb_blastdb_masked_info", "swb_blastdb_open", "swb_blastdb_seqlen", "swb_blastdb_sequence",
            "swb_blastdb_title", "swb_db_close", "swb_db_info", "swb_db_open",
-           "swb_db_open_async", "swb_db_open_blast", "swb_db_open_blast_translated", "swb_db_open_ms",
+           "swb_db_open_async", "swb_db_open_blast", "swb_db_open_blast_translated", "swb_db_open_ms", "swb_db_set_filter",
            "swb_db_wait", "swb_defline_text", "swb_device_count", "swb_gencode_name",
            "swb_host_alloc", "swb_host_free", "swb_last_cuda_error", "swb_matrix_builtin",
            "swb_matrix_limits", "swb_matrix_nucleotide", "swb_matrix_parse", "swb_matrix_read",
@@ -100,6 +100,8 @@ def load_library():
     lib.swb_hits_merge.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), p64, C.c_int64,
                                    C.c_void_p, C.c_void_p]
     lib.swb_set_cache_limit.restype = C.c_int
+    lib.swb_db_set_filter.restype = C.c_int
+    lib.swb_db_set_filter.argtypes = [C.c_void_p, C.c_void_p]
     lib.swb_alu_peak.restype = C.c_int
     lib.swb_alu_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.swb_set_cache_limit.argtypes = [C.c_int64]
@@ -113,7 +115,7 @@ def load_library():
     lib.swb_set_geometry.restype = C.c_int
     for name in ("swb_device_count", "swb_host_alloc", "swb_host_free", "swb_db_open",
                  "swb_db_close", "swb_db_info", "swb_search", "swb_search_list", "swb_search_end",
-                 "swb_set_mode", "swb_db_open_ms", "swb_set_shape", "swb_db_open_async", "swb_db_wait"):
+                 "swb_set_mode", "swb_db_open_ms", "swb_db_set_filter", "swb_set_shape", "swb_db_open_async", "swb_db_wait"):
         getattr(lib, name).restype = C.c_int
     lib.swb_blastdb_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.swb_blastdb_close.argtypes = [C.c_void_p]
@@ -327,6 +329,14 @@ class Database:
 
     def set_mode(self, mode):
         _check(self._lib.swb_set_mode(self._h, int(mode)))
+
+    def set_filter(self, include=None):
+        """swb_db_set_filter: include = boolean array over the subjects (None removes the filter)."""
+        if include is None:
+            _check(self._lib.swb_db_set_filter(self._h, None))
+            return
+        bits = np.packbits(np.asarray(include, dtype=bool), bitorder="little")
+        _check(self._lib.swb_db_set_filter(self._h, bits.ctypes.data))
 
     def set_geometry(self, geometry=0):
         _check(self._lib.swb_set_geometry(self._h, int(geometry)))

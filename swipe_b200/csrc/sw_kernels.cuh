@@ -1224,9 +1224,17 @@ __global__ void swb_requeue_codes_kernel(const long long *requeue, long long n, 
 
 // counts: [0..2] subjects the reference's 7 / 16 / 63-bit pass would have kept, [3] totalhits
 // (score >= min_score), [4] obvious (score > upper)
+// filter: one bit per subject (bit k & 7 of byte k >> 3), a clear bit keeps the subject out of the sink
+// (the reference's db_check_inclusion, swipe.cc:1373-1376); NULL = every subject takes part
+__device__ __forceinline__ bool swb_included(const unsigned char *filter, long long k)
+{
+  return !filter || ((filter[k >> 3] >> (k & 7)) & 1);
+}
+
 __global__ void __launch_bounds__(256) swb_hist_kernel(const long long *scores, long long n,
                                                         long long limit7, long long limit16,
                                                         long long min_score, long long upper,
+                                                        const unsigned char *filter,
                                                         unsigned long long *counts, unsigned *hist)
 {
   __shared__ unsigned sh[SWB_HIST_BINS];
@@ -1240,6 +1248,7 @@ __global__ void __launch_bounds__(256) swb_hist_kernel(const long long *scores, 
   {
     const long long v = scores[k];
     if (v < limit7) w7++; else if (v < limit16) w16++; else w63++;
+    if (!swb_included(filter, k)) continue;
     tot += v >= min_score;
     obv += v > upper;
     if (v >= min_score && v <= upper)
@@ -1300,6 +1309,7 @@ __global__ void __launch_bounds__(1024) swb_cut_kernel(const unsigned *hist, lon
 // cand[slot] = score << 32 | subject for every admissible score whose bin is >= cut[0]
 __global__ void __launch_bounds__(256) swb_compact_kernel(const long long *scores, long long n,
                                                            long long min_score, long long upper,
+                                                           const unsigned char *filter,
                                                            const unsigned *cut, unsigned long long *cand,
                                                            unsigned long long *ncand)
 {
@@ -1311,7 +1321,7 @@ __global__ void __launch_bounds__(256) swb_compact_kernel(const long long *score
   {
     v = scores[k];
     const long long bin = v > SWB_HIST_BINS - 1 ? SWB_HIST_BINS - 1 : v;
-    take = v >= min_score && v <= upper && bin >= c;
+    take = v >= min_score && v <= upper && bin >= c && swb_included(filter, k);
   }
   const unsigned m = __ballot_sync(0xffffffffu, take);
   if (!m) return;

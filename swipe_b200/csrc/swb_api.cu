@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -242,6 +243,9 @@ struct swb_db
   DevBuf<unsigned char> he;
   DevBuf<uint4> bndH, bndF;
   DevBuf<int> slot_flags;         // multi-pass scratch regions in use (ScanParams::slot_flags)
+  DevBuf<unsigned char> filter;   // swb_db_set_filter: one bit per subject, honoured by the device sink
+  std::vector<unsigned char> h_filter;
+  bool has_filter = false;
   DevBuf<ScanSeg> segs;           // chunk table of a merged (whole-shard) scan launch
   DevBuf<unsigned> hist;          // [SWB_HIST_BINS] admissible scores, [SWB_HIST_BINS] = the cut bin
   DevBuf<unsigned long long> cand, cand_sorted;   // score << 32 | subject of the candidates
@@ -960,8 +964,9 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     SWB_TRY(db->cand.reserve((size_t)n));
     SWB_CUDA(cudaMemsetAsync(db->hist.p, 0, (SWB_HIST_BINS + 1) * sizeof(unsigned), st));
     const unsigned hgrid = (unsigned)std::min<long long>((n + 256 * 16 - 1) / (256 * 16), (long long)db->sm_count * 8);
+    const unsigned char *filter = db->has_filter ? db->filter.p : nullptr;
     swb_hist_kernel<<<std::max(hgrid, 1u), 256, 0, st>>>(db->scores.p, n, tb.limit7, tb.limit16, hits->min_score,
-                                                         hits->upper, db->counters.p + 1, db->hist.p);
+                                                         hits->upper, filter, db->counters.p + 1, db->hist.p);
     SWB_CUDA(cudaGetLastError());
     swb_cut_kernel<<<1, 1024, 0, st>>>(db->hist.p, hits->keep, db->hist.p + SWB_HIST_BINS);
     SWB_CUDA(cudaGetLastError());
@@ -970,7 +975,8 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     if (hits->keep > 0)
     {
       swb_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-          db->scores.p, n, hits->min_score, hits->upper, db->hist.p + SWB_HIST_BINS, db->cand.p, db->counters.p + 6);
+          db->scores.p, n, hits->min_score, hits->upper, filter, db->hist.p + SWB_HIST_BINS, db->cand.p,
+          db->counters.p + 6);
       SWB_CUDA(cudaGetLastError());
       launches++;
     }
@@ -1055,7 +1061,14 @@ int search_impl(swb_db *db, const unsigned char *query, long long qlen, const sw
     }
     if (hits)
     {
-      const int64_t *arr[1] = {(const int64_t *)scores};
+      std::vector<long long> kept;             // the host sink of the wide-cell path under a subject filter
+      if (db->has_filter)
+      {
+        kept.assign(scores, scores + n);
+        for (long long k = 0; k < n; k++)
+          if (!((db->h_filter[(size_t)(k >> 3)] >> (k & 7)) & 1)) kept[(size_t)k] = LLONG_MIN;
+      }
+      const int64_t *arr[1] = {(const int64_t *)(db->has_filter ? kept.data() : scores)};
       const int64_t cnt[1] = {n}, base[1] = {hits->seqno_base};
       int64_t tot = 0, obv = 0;
       const int64_t k = swb_topk_merge(1, arr, cnt, base, hits->keep, hits->min_score, hits->upper,
@@ -1891,7 +1904,7 @@ int swb_db_close(swb_db *db)
   db->scores.release(); db->bestpos.release(); db->bestq.release(); db->requeue.release();
   db->list.release(); db->counters.release(); db->he.release(); db->bndH.release();
   db->bndF.release(); db->segs.release();
-  db->slot_flags.release();
+  db->slot_flags.release(); db->filter.release();
   db->hist.release(); db->cand.release(); db->cand_sorted.release(); db->sort_tmp.release();
   for (int i = 0; i < 4; i++)
     if (db->ev[i]) cudaEventDestroy(db->ev[i]);
@@ -1952,6 +1965,26 @@ int swb_search_hits(swb_db *db, const uint8_t *query, int64_t qlen, const swb_sc
   *nhits = H.nhits;
   if (totalhits) *totalhits = H.totalhits;
   if (obvious) *obvious = H.obvious;
+  return SWB_OK;
+}
+
+int swb_db_set_filter(swb_db *db, const uint8_t *bitmap)
+{
+  if (!db) return SWB_ERR_ARG;
+  SWB_CUDA(cudaSetDevice(db->device));
+  SWB_CUDA(cudaStreamSynchronize(db->stream));              // no search of this handle is using the old one
+  if (!bitmap)
+  {
+    db->has_filter = false;
+    return SWB_OK;
+  }
+  const size_t bytes = (size_t)((db->nseq + 7) / 8);
+  db->h_filter.assign(bitmap, bitmap + bytes);
+  SWB_TRY(db->filter.reserve(std::max<size_t>(bytes, 1)));
+  if (bytes)
+    SWB_CUDA(cudaMemcpyAsync(db->filter.p, db->h_filter.data(), bytes, cudaMemcpyHostToDevice, db->stream));
+  SWB_CUDA(cudaStreamSynchronize(db->stream));
+  db->has_filter = true;
   return SWB_OK;
 }
 

@@ -502,3 +502,34 @@ def test_device_sink_wide_cells(oracle):
     with Database(residues, offsets) as db:
         seq, s, tot, obv = db.search_hits(q, sc, 20, 1)
     assert np.array_equal(seq, oseq) and np.array_equal(s, osc) and (tot, obv) == (otot, oobv)
+
+
+def test_device_sink_subject_filter(oracle):
+    """swb_db_set_filter: subjects whose bit is clear are scored but never enter the hit list nor the
+    totalhits / obvious counts (db_check_inclusion before the kernels, swipe.cc:1373-1376) -- the list
+    equals the oracle's sink over the included subjects only; dense scores ignore the filter; NULL
+    removes it.  Narrow cells (device sink) and 64-bit cells (host sink inside the library)."""
+    q = synth.protein_query(120, seed=91)
+    residues, offsets = synth.protein_db(2500, query=q, seed=92, plant_every=30, max_len=400)
+    rng = np.random.default_rng(93)
+    include = rng.random(2500) < 0.4
+    include[::30] = rng.random(include[::30].size) < 0.5          # planted subjects on both sides
+    idx = np.flatnonzero(include)
+    for open_, ext in ((11, 1), (2 ** 31, 2 ** 31)):
+        sc = Scoring(B62, open_, ext)
+        exp = oracle.scan(residues, offsets, q, B62, open_, ext)[0]
+        want = oracle.topk(idx, exp[idx], 25, min_score=1, upper=200)
+        everything = oracle.topk(np.arange(exp.size), exp, 25, min_score=1, upper=200)
+        with Database(residues, offsets) as db:
+            db.set_filter(include)
+            seq, s, tot, obv = db.search_hits(q, sc, 25, 1, 200)
+            assert np.array_equal(seq, want[0]) and np.array_equal(s, want[1]) and (tot, obv) == want[2:]
+            assert db.last_counters["ref_width7"] + db.last_counters["ref_width16"] \
+                + db.last_counters["ref_width63"] == exp.size
+            assert np.array_equal(db.search(q, sc), exp)
+            if open_ == 11:
+                got = db.search_hits_batch([q, q[:50]], sc, 25, 1, 200)
+                assert np.array_equal(got[0][0], want[0]) and np.array_equal(got[0][1], want[1])
+            db.set_filter(None)
+            seq, s, tot, obv = db.search_hits(q, sc, 25, 1, 200)
+            assert np.array_equal(seq, everything[0]) and (tot, obv) == everything[2:]
