@@ -128,6 +128,7 @@ def test_batch_and_sink_argument_checks_do_not_need_a_gpu():
     assert lib.swb_search_hits_batch(None, -1, None, None, None, 0, 1, 0, 0, None, None, None, None, None, None) == -1
     assert lib.swb_set_cache_limit(-5) == -1 and lib.swb_set_cache_limit(8 << 30) == 0
     assert lib.swb_set_geometry(None, 1) == -1
+    assert lib.swb_db_set_filter(None, None) == -1
     assert lib.swb_alu_peak(0, None, None) == -1
 
 
