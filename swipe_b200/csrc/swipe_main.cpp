@@ -267,6 +267,8 @@ struct Shard
   int device = 0;
   int64_t first = 0, count = 0;         // source sequences of the BLAST database
   swb_db *db = nullptr;
+  bool sink_filter = false;             // mask / -x list handed to the device sink (swb_db_set_filter)
+  int64_t nincluded = 0;                // sequences of the shard that pass it
 };
 
 struct Run
@@ -342,15 +344,15 @@ void search_shard(Run &R, const Query &q, Shard &S)
     {
       const std::vector<uint8_t> &qv = query_variant(R, q, qstrand, qframe);
       const bool filtered = R.memb_bit != 0 || !R.taxids.empty();
-      if (!filtered && unit == 1 && R.keephits > 0)
+      if ((!filtered || S.sink_filter) && unit == 1 && R.keephits > 0)
       {
-        // every subject takes part and subject = sequence: the sink runs on the device
-        // (swb_search_hits) and only the hits hits_enter would have kept come back
+        // subject = sequence, and every subject takes part or the device knows which do: the sink runs
+        // on the device (swb_search_hits) and only the hits hits_enter would have kept come back
         std::vector<int64_t> hs((size_t)R.keephits), hv((size_t)R.keephits);
         int64_t nh = 0, t = 0, ob = 0;
         check(swb_search_hits(S.db, qv.data(), (int64_t)qv.size(), &sc, S.first, R.keephits, R.st.score_threshold,
                               R.st.upper_threshold, hs.data(), hv.data(), &nh, &t, &ob, nullptr), "search");
-        computed += nsub;
+        computed += filtered ? (o.view == 99 ? S.nincluded : 0) : nsub;        // as the dense path below counts
         tot += t;
         obv += ob;
         for (int64_t k = 0; k < nh; k++)
@@ -1295,6 +1297,19 @@ int main(int argc, char **argv)
         rcs[g] = R.translated_db
                      ? swb_db_open_blast_translated(S.device, R.bdb, S.first, S.count, R.dtable, 0, nullptr, &S.db)
                      : swb_db_open_blast(S.device, R.bdb, S.first, S.count, 0, nullptr, &S.db);
+        if (rcs[g] == SWB_OK && !R.translated_db && (R.memb_bit != 0 || !R.taxids.empty()))
+        {
+          // db_check_inclusion once per sequence (swipe.cc:1373-1376), as one bit each for the device sink
+          std::vector<uint8_t> bits((size_t)(S.count + 7) / 8 + 1, 0);
+          for (int64_t j = 0; j < S.count; j++)
+            if (included(R, S.first + j))
+            {
+              bits[(size_t)(j >> 3)] |= (uint8_t)(1u << (j & 7));
+              S.nincluded++;
+            }
+          rcs[g] = swb_db_set_filter(S.db, bits.data());
+          S.sink_filter = rcs[g] == SWB_OK;
+        }
       });
     for (std::thread &t : pool) t.join();
     for (int rc : rcs) check(rc, "uploading the database");
